@@ -1,0 +1,156 @@
+/* ias_b200.h -- C ABI of libias_b200.so: the B200 (sm_100a) front end of inverse-audio-synthesis.
+ *
+ * The reference (turian/inverse-audio-synthesis) has no FFI of its own: its hot path is three Python class
+ * surfaces.  Each entry point below is the device-side replacement a binding for one of those
+ * surfaces calls; the reference interface it replaces is cited as file:line into /root/reference (torchsynth call
+ * sites where the code lives in the un-vendored torchsynth package).  ias_b200/{voice,pqmf,vicreg}.py are the
+ * ctypes bindings; INTEGRATION.md shows the stub a maintainer adds to the reference.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - tensors are contiguous row-major fp32; pointers 16-byte aligned;
+ *   - nothing is allocated per call: scratch comes in through (workspace, workspace_bytes);
+ *   - work is enqueued on `stream` (a cudaStream_t) with no hidden synchronisation;
+ *   - return 0 on success, an IAS_ERR_* code otherwise, message in ias_last_error() (thread local);
+ *   - never throws, never exits.  One host thread per device at a time.
+ */
+#ifndef IAS_B200_H
+#define IAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IAS_OK 0
+#define IAS_ERR_INVALID 1     /* bad argument */
+#define IAS_ERR_CUDA 2        /* CUDA runtime error (launch, memcpy) */
+#define IAS_ERR_UNSUPPORTED 3 /* shape outside what the kernels cover */
+#define IAS_ERR_WORKSPACE 4   /* workspace missing or too small */
+#define IAS_ERR_NCCL 5        /* NCCL error */
+
+#define IAS_VOICE_NPARAMS 78   /* conf/config.yaml:27 */
+#define IAS_VOICE_NCONTROL 5   /* vco_1_pitch, vco_1_amp, vco_2_pitch, vco_2_amp, noise_amp */
+#define IAS_NCCL_ID_BYTES 128
+
+typedef void* ias_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define IAS_API __attribute__((visibility("default")))
+#else
+#define IAS_API
+#endif
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+IAS_API int ias_version(void);
+IAS_API const char* ias_last_error(void);
+/* IAS_OK iff `device` is a compute-capability 10.x GPU (the only target). */
+IAS_API int ias_device_check(int device);
+
+/* Launch counter and optional per-kernel CUDA-event timing (bench.py's roofline leg).  Every kernel launch the
+ * library makes is counted; with profiling enabled each launch is also bracketed by an event pair on its stream. */
+IAS_API int ias_prof_enable(int on);
+IAS_API int ias_prof_reset(void);
+IAS_API int ias_prof_kernel_count(void);
+IAS_API const char* ias_prof_kernel_name(int id);
+IAS_API long long ias_prof_launches(int id); /* id < 0: all kernels */
+IAS_API int ias_prof_read(int id, double* total_ms, long long* timed_launches); /* synchronises on the events */
+
+/* ---- Voice: torchsynth.synth.Voice (vicreg_audio_params.py:86-94,114; audio_to_params.py:196-203,215,238-257) --
+ * Parameter block layout used by every voice entry point: params01[78][B], parameter-major, rows in torchsynth
+ * *registration* order (= nn.Module.parameters() order = columns of the `params` tensor Voice.forward returns). */
+
+/* "module/param" of registration row `reg_index` (0..77), NULL if out of range. */
+IAS_API const char* ias_voice_param_name(int reg_index);
+/* Position of registration row `reg_index` in sorted(named_parameters()), the order randomize(seed) assigns. */
+IAS_API int ias_voice_sorted_index(int reg_index);
+
+/* AbstractSynth.randomize(seed) + _batch_idx_to_is_train: sound i of the batch gets the first 78 outputs of
+ * torch's CPU MT19937 seeded with (first_sound_id + i) (bit-identical to torch.rand(78, generator=g)).
+ * Rows whose frozen78_host[row] != 0 are left untouched (freeze_parameters); frozen78_host may be NULL.
+ * is_train[B] (uint8) may be NULL.  first_sound_id = batch_idx * batch_size. */
+IAS_API int ias_voice_seed_params(int64_t first_sound_id, int B, const uint8_t* frozen78_host, float* params01,
+                          uint8_t* is_train, ias_stream_t stream);
+
+IAS_API size_t ias_voice_workspace_bytes(int B, int T, int C);
+
+/* Control-rate stage only (keyboard, 6 ADSR, 2 LFO, modulation matrix): ctrl[B][5][C].  Inspection entry point
+ * used by the parity tests; ias_voice_render runs the same kernel internally. */
+IAS_API int ias_voice_control(const float* params01, int B, int C, float control_rate, float eps, float* ctrl,
+                      void* workspace, size_t workspace_bytes, ias_stream_t stream);
+
+/* Voice.output(): params -> audio[B][T].  noise[noise_rows][T] is the Noise module buffer (row b uses
+ * noise[b % noise_rows]).  peak[B] receives max|mixed| before normalisation (may be NULL).  normalize != 0 applies
+ * util.normalize_if_clipping (x / peak where peak > 1); normalize == 0 leaves the raw mix so a consumer can fold
+ * the scale in.  Two inspection hooks for the parity tests, both normally NULL: ctrl_in[B][5][C] replaces the
+ * control-rate signals the audio stage reads (the per-voice constants still come from params01), and phase_dbg
+ * receives the two VCO cosine arguments, [B][2][T]. */
+IAS_API int ias_voice_render(const float* params01, const float* noise, int noise_rows, float* audio, float* peak, int B,
+                     int T, int C, float sample_rate, float control_rate, float eps, int normalize,
+                     const float* ctrl_in, float* phase_dbg, void* workspace, size_t workspace_bytes,
+                     ias_stream_t stream);
+
+/* ---- PQMF: pqmf.PQMF (pqmf.py:9-55; callers audioembed.py:38, vicreg_audio_params.py:40) ----------------- */
+
+/* Output length of analysis: floor((T + 2*((K-1)/2) - K) / N) + 1 with K = taps + 1 (pqmf.py:49-50). */
+IAS_API int ias_pqmf_out_len(int T, int N, int K);
+
+/* PQMF.analysis / forward (pqmf.py:46-50): out[b][k][n] = sum_j H[k][j] * x[b][n*N + j - (K-1)/2].
+ * H is the module buffer H[:,0,:] = [N][K]; H_host is the same values in host memory (fast paths pass the taps
+ * as kernel arguments); H_dev is used when H_host is NULL or the shape has no specialised kernel.
+ * row_scale[B] (may be NULL) multiplies row b of x, so normalize_if_clipping can be folded in (scale = 1/peak). */
+IAS_API int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* row_scale, float* out,
+                      int B, int T, int N, int K, ias_stream_t stream);
+
+/* PQMF.synthesis (pqmf.py:52-55): zero-stuff by N with gain N, then the N->1 FIR G = [N][K] (buffer G[0]).
+ * y[b][t], t < L*N. */
+IAS_API int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, float* y, int B, int L, int N, int K,
+                       ias_stream_t stream);
+
+/* ---- VICReg loss: vicreg.VICReg.loss / off_diagonal (vicreg.py:35-58,73-76) ------------------------------ */
+
+IAS_API size_t ias_vicreg_workspace_bytes(int B, int D);
+
+/* x, y: [B][D] (the gathered batch when distributed).  Rows [local_row0, local_row0 + B_local) are this rank's own
+ * and are the only ones in the invariance term (vicreg.py:36 precedes the gather at vicreg.py:38-39).
+ * cfg_batch_size is cfg.vicreg.batch_size (covariance divisor, vicreg.py:47-48), embeddim is cfg.embeddim
+ * (vicreg.py:49).  out4 (device) = {loss, repr_loss, std_loss, cov_loss}.  The workspace keeps what
+ * ias_vicreg_loss_backward needs until the next forward call on it. */
+IAS_API int ias_vicreg_loss(const float* x, const float* y, int B, int local_row0, int B_local, int cfg_batch_size, int D,
+                    int embeddim, float sim_coeff, float std_coeff, float cov_coeff, float* out4, void* workspace,
+                    size_t workspace_bytes, ias_stream_t stream);
+
+/* d out4 . gout4 / d x, d y for the same arguments as the preceding ias_vicreg_loss on `workspace`.
+ * gout4 (device) holds the upstream gradients of {loss, repr, std, cov}.  gx, gy: [B][D]; rows outside the local
+ * range receive only the std/cov contributions (FullGatherLayer.backward then reduce-scatters them). */
+IAS_API int ias_vicreg_loss_backward(const float* x, const float* y, int B, int local_row0, int B_local, int cfg_batch_size,
+                             int D, int embeddim, float sim_coeff, float std_coeff, float cov_coeff,
+                             const float* gout4, float* gx, float* gy, void* workspace, size_t workspace_bytes,
+                             ias_stream_t stream);
+
+/* Test hook: plain CUDA-core Gram of the centred matrix, gram[D][D] = xc^T xc, to cross-check the tcgen05 path. */
+IAS_API int ias_vicreg_gram_reference(const float* x, int B, int D, float* gram, void* workspace, size_t workspace_bytes,
+                              ias_stream_t stream);
+/* Test hook: the tcgen05 Gram alone (same workspace).  Needs D % 128 == 0; gram holds [2][D][D] floats (the hook
+ * runs x as both sides; use the first [D][D]). */
+IAS_API int ias_vicreg_gram_tc(const float* x, int B, int D, float* gram, void* workspace, size_t workspace_bytes,
+                       ias_stream_t stream);
+
+/* ---- Embedding all-gather: vicreg.FullGatherLayer (vicreg.py:79-95; intended call vicreg.py:38-39) ------- */
+
+/* These five live in libias_comm.so (links NCCL); ias_comm_last_error() is that library's error string. */
+IAS_API const char* ias_comm_last_error(void);
+IAS_API int ias_comm_unique_id(void* id128_host);
+IAS_API int ias_comm_init(const void* id128_host, int rank, int world, void** comm);
+IAS_API int ias_comm_destroy(void* comm);
+/* forward: all[W][count] <- every rank's local[count] in rank order. */
+IAS_API int ias_comm_allgather(void* comm, const float* local, float* all, size_t count, ias_stream_t stream);
+/* backward: local[count] <- sum over ranks of their all[W][count], own slice (all-reduce + slice == reduce-scatter). */
+IAS_API int ias_comm_reduce_scatter(void* comm, const float* all, float* local, size_t count, ias_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IAS_B200_H */

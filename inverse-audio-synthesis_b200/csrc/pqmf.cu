@@ -1,0 +1,363 @@
+// PQMF analysis / synthesis for sm_100a.
+//
+// Replaces pqmf.PQMF.analysis / forward (pqmf.py:46-50: F.conv1d(x, H, padding=taps//2, stride=N)) and
+// pqmf.PQMF.synthesis (pqmf.py:52-55: conv_transpose1d zero-stuffing with gain N, then F.conv1d with G).
+//
+// Both directions are register-tiled FIR kernels.  A thread owns Q consecutive decimated time steps for all N
+// bands, so every input sample it needs is read from shared memory into a register once and then used by all
+// (up to 63) taps that touch it; the taps are kernel arguments, i.e. live in the constant bank and are FFMA
+// operands with no load instruction.  The signal tile is staged global -> shared with 128-bit coalesced loads
+// and a padded layout (stride Q*N made odd) so the per-thread sliding windows are bank-conflict free.  The
+// zero-stuffed [B,N,L*N] intermediate of the reference's synthesis is never materialised (polyphase indexing).
+// HBM traffic: 4T read + 4T written per sound in each direction (algorithmic minimum).
+#include "ias_common.cuh"
+
+namespace ias {
+namespace {
+
+constexpr int PQ_THREADS = 128;
+
+template <int N, int K>
+struct Taps {
+  float h[N * K];
+};
+
+__host__ __device__ constexpr int odd_stride(int s) { return (s & 1) ? s : s + 1; }
+
+// ------------------------------------------------------------------------------------------------------------
+// analysis: out[b][k][n] = sum_j H[k][j] * x[b][n*N + j - PAD]
+// ------------------------------------------------------------------------------------------------------------
+template <int N, int K, int Q>
+__global__ void __launch_bounds__(PQ_THREADS)
+k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale, float* __restrict__ out, int T, int L,
+                int tiles_per_row, Taps<N, K> taps) {
+  constexpr int PAD = (K - 1) / 2;
+  constexpr int S = Q * N;                 // input samples consumed per thread
+  constexpr int SP = odd_stride(S);        // padded stride in shared memory
+  constexpr int WIN = (Q - 1) * N + K;     // input window of one thread
+  constexpr int TILE_N = PQ_THREADS * Q;   // output steps per CTA
+  constexpr int SPAN = TILE_N * N + K - N + 4;  // staged samples (incl. up to 3 alignment samples, rounded)
+  constexpr int SPAN4 = (SPAN + 3) / 4;
+  __shared__ float xs[(SPAN4 * 4 / S + 2) * SP];
+
+  const int b = blockIdx.x / tiles_per_row;
+  const int tile = blockIdx.x - b * tiles_per_row;
+  const int n_tile = tile * TILE_N;
+  const float* xr = x + (size_t)b * T;
+  const float scale = row_scale ? row_scale[b] : 1.0f;
+
+  // staged window starts at g0 (multiple of 4, <= first needed sample)
+  const int first = n_tile * N - PAD;
+  const int off = ((first % 4) + 4) % 4;
+  const int g0 = first - off;
+  const bool vec_ok = ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+  for (int i4 = threadIdx.x; i4 < SPAN4; i4 += PQ_THREADS) {
+    const int g = g0 + 4 * i4;
+    float4 v;
+    if (vec_ok && g >= 0 && g + 3 < T) {
+      v = __ldg(reinterpret_cast<const float4*>(xr + g));
+    } else {
+      v.x = (g + 0 >= 0 && g + 0 < T) ? __ldg(xr + g + 0) : 0.0f;
+      v.y = (g + 1 >= 0 && g + 1 < T) ? __ldg(xr + g + 1) : 0.0f;
+      v.z = (g + 2 >= 0 && g + 2 < T) ? __ldg(xr + g + 2) : 0.0f;
+      v.w = (g + 3 >= 0 && g + 3 < T) ? __ldg(xr + g + 3) : 0.0f;
+    }
+    const float e[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = 4 * i4 + c;
+      xs[(i / S) * SP + (i % S)] = e[c];
+    }
+  }
+  __syncthreads();
+
+  // sliding window of this thread into registers
+  float w[WIN];
+  {
+    const int base = threadIdx.x * S + off;  // tile-local index of x[n0*N - PAD]
+#pragma unroll
+    for (int c = 0; c < WIN; ++c) {
+      const int i = base + c;
+      w[c] = xs[(i / S) * SP + (i % S)];
+    }
+  }
+  float acc[Q][N];
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[q][k] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.h[k * K + j], w[q * N + j], acc[q][k]);
+
+  const int n0 = n_tile + threadIdx.x * Q;
+  float* ob = out + (size_t)b * N * L;
+  const bool st_vec = ((L & 3) == 0) && (Q % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float* o = ob + (size_t)k * L + n0;
+    if (st_vec && n0 + Q <= L) {
+#pragma unroll
+      for (int q = 0; q < Q; q += 4)
+        *reinterpret_cast<float4*>(o + q) = make_float4(acc[q][k], acc[q + 1][k], acc[q + 2][k], acc[q + 3][k]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (n0 + q < L) o[q] = acc[q][k];
+    }
+  }
+}
+
+// Any (N, K): one thread per output, taps from global memory.  Correct for shapes without a specialised kernel.
+__global__ void k_pqmf_analysis_generic(const float* __restrict__ x, const float* __restrict__ H,
+                                        const float* __restrict__ row_scale, float* __restrict__ out, int B, int T,
+                                        int N, int K, int L) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * N * L;
+  if (idx >= total) return;
+  const int n = (int)(idx % L);
+  const int k = (int)((idx / L) % N);
+  const int b = (int)(idx / ((size_t)L * N));
+  const int pad = (K - 1) / 2;
+  const float* xr = x + (size_t)b * T;
+  const float scale = row_scale ? row_scale[b] : 1.0f;
+  float acc = 0.0f;
+  for (int j = 0; j < K; ++j) {
+    const int g = n * N + j - pad;
+    if (g >= 0 && g < T) acc = fmaf(H[k * K + j], xr[g] * scale, acc);
+  }
+  out[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// synthesis: y[b][n*N + p] = sum_k sum_{j : p(j) = p} G[k][j] * (N * z[b][k][n + o(j)])
+//   p(j) = (PAD - j) mod N,  o(j) = (p(j) + j - PAD) / N   (tap j only ever meets a non-zero of the zero-stuffed
+//   signal on output phase p(j))
+// ------------------------------------------------------------------------------------------------------------
+template <int N, int K>
+struct SynthGeom {
+  static constexpr int PAD = (K - 1) / 2;
+  // tap j contributes to output phase p(j) with source offset o(j): y[n*N + p] += G[k][j] * N*z[k][n + o]
+  __host__ __device__ static constexpr int phase(int j) { return (((PAD - j) % N) + N) % N; }
+  __host__ __device__ static constexpr int offset(int j) { return (phase(j) + j - PAD) / N; }  // exact division
+  __host__ __device__ static constexpr int omin() {
+    int m = 1000000;
+    for (int j = 0; j < K; ++j) m = offset(j) < m ? offset(j) : m;
+    return m;
+  }
+  __host__ __device__ static constexpr int omax() {
+    int m = -1000000;
+    for (int j = 0; j < K; ++j) m = offset(j) > m ? offset(j) : m;
+    return m;
+  }
+};
+
+template <int N, int K, int Q>
+__global__ void __launch_bounds__(PQ_THREADS)
+k_pqmf_synthesis(const float* __restrict__ z, float* __restrict__ y, int L, int tiles_per_row, Taps<N, K> taps) {
+  using Geo = SynthGeom<N, K>;
+  constexpr int DMIN = Geo::omin();
+  constexpr int WIN = Q + Geo::omax() - DMIN;  // per-band window of one thread: n0+DMIN .. n0+Q-1+omax
+  constexpr int SP = odd_stride(Q);
+  constexpr int TILE_N = PQ_THREADS * Q;
+  constexpr int SPAN = TILE_N + WIN - Q + 4;
+  constexpr int SPAN4 = (SPAN + 3) / 4;
+  constexpr int ROW = (SPAN4 * 4 / Q + 2) * SP;
+  __shared__ float zs[N * ROW];
+
+  const int b = blockIdx.x / tiles_per_row;
+  const int tile = blockIdx.x - b * tiles_per_row;
+  const int n_tile = tile * TILE_N;
+  const int first = n_tile + DMIN;
+  const int off = ((first % 4) + 4) % 4;
+  const int g0 = first - off;
+  const bool vec_ok = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
+  const float gain = (float)N;
+  for (int k = 0; k < N; ++k) {
+    const float* zr = z + ((size_t)b * N + k) * L;
+    for (int i4 = threadIdx.x; i4 < SPAN4; i4 += PQ_THREADS) {
+      const int g = g0 + 4 * i4;
+      float4 v;
+      if (vec_ok && g >= 0 && g + 3 < L) {
+        v = __ldg(reinterpret_cast<const float4*>(zr + g));
+      } else {
+        v.x = (g + 0 >= 0 && g + 0 < L) ? __ldg(zr + g + 0) : 0.0f;
+        v.y = (g + 1 >= 0 && g + 1 < L) ? __ldg(zr + g + 1) : 0.0f;
+        v.z = (g + 2 >= 0 && g + 2 < L) ? __ldg(zr + g + 2) : 0.0f;
+        v.w = (g + 3 >= 0 && g + 3 < L) ? __ldg(zr + g + 3) : 0.0f;
+      }
+      const float e[4] = {v.x * gain, v.y * gain, v.z * gain, v.w * gain};  // fp32 N*z like conv_transpose1d
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = 4 * i4 + c;
+        zs[k * ROW + (i / Q) * SP + (i % Q)] = e[c];
+      }
+    }
+  }
+  __syncthreads();
+
+  float acc[Q][N];
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+#pragma unroll
+    for (int p = 0; p < N; ++p) acc[q][p] = 0.0f;
+
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float w[WIN];
+    const int base = threadIdx.x * Q + off;  // tile-local index of z[n0 + DMIN]
+#pragma unroll
+    for (int c = 0; c < WIN; ++c) {
+      const int i = base + c;
+      w[c] = zs[k * ROW + (i / Q) * SP + (i % Q)];
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float g = taps.h[k * K + j];
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        acc[q][Geo::phase(j)] = fmaf(g, w[q + Geo::offset(j) - DMIN], acc[q][Geo::phase(j)]);
+    }
+  }
+
+  const int n0 = n_tile + threadIdx.x * Q;
+  float* yo = y + (size_t)b * L * N + (size_t)n0 * N;
+  const bool st_vec = (((size_t)L * N) % 4 == 0) && ((Q * N) % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+  if (st_vec && n0 + Q <= L) {
+    float flat[Q * N];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int p = 0; p < N; ++p) flat[q * N + p] = acc[q][p];
+#pragma unroll
+    for (int c = 0; c < Q * N; c += 4)
+      *reinterpret_cast<float4*>(yo + c) = make_float4(flat[c], flat[c + 1], flat[c + 2], flat[c + 3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+      if (n0 + q < L) {
+#pragma unroll
+        for (int p = 0; p < N; ++p) yo[q * N + p] = acc[q][p];
+      }
+  }
+}
+
+__global__ void k_pqmf_synthesis_generic(const float* __restrict__ z, const float* __restrict__ G,
+                                         float* __restrict__ y, int B, int L, int N, int K) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t Tout = (size_t)L * N;
+  if (idx >= (size_t)B * Tout) return;
+  const int b = (int)(idx / Tout);
+  const long long t = (long long)(idx % Tout);
+  const int pad = (K - 1) / 2;
+  const float gain = (float)N;
+  float acc = 0.0f;
+  for (int k = 0; k < N; ++k) {
+    const float* zr = z + ((size_t)b * N + k) * L;
+    for (int j = 0; j < K; ++j) {
+      const long long m = t + j - pad;
+      if (m >= 0 && m < (long long)Tout && (m % N) == 0) acc = fmaf(G[k * K + j], zr[m / N] * gain, acc);
+    }
+  }
+  y[idx] = acc;
+}
+
+template <int N, int K, int Q>
+int launch_analysis(const float* x, const float* H_host, const float* row_scale, float* out, int B, int T, int L,
+                    cudaStream_t st) {
+  Taps<N, K> taps;
+  for (int i = 0; i < N * K; ++i) taps.h[i] = H_host[i];
+  constexpr int TILE_N = PQ_THREADS * Q;
+  const int tiles = (L + TILE_N - 1) / TILE_N;
+  {
+    ProfScope prof_(K_PQMF_ANALYSIS, st);
+    k_pqmf_analysis<N, K, Q><<<(unsigned)((size_t)B * tiles), PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_analysis");
+  return IAS_OK;
+}
+
+template <int N, int K, int Q>
+int launch_synthesis(const float* z, const float* G_host, float* y, int B, int L, cudaStream_t st) {
+  Taps<N, K> taps;
+  for (int i = 0; i < N * K; ++i) taps.h[i] = G_host[i];
+  constexpr int TILE_N = PQ_THREADS * Q;
+  const int tiles = (L + TILE_N - 1) / TILE_N;
+  {
+    ProfScope prof_(K_PQMF_SYNTHESIS, st);
+    k_pqmf_synthesis<N, K, Q><<<(unsigned)((size_t)B * tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_synthesis");
+  return IAS_OK;
+}
+
+}  // namespace
+}  // namespace ias
+
+using namespace ias;
+
+extern "C" int ias_pqmf_out_len(int T, int N, int K) {
+  if (T <= 0 || N <= 0 || K <= 0) return -1;
+  const int pad = (K - 1) / 2;
+  const int span = T + 2 * pad - K;
+  return span < 0 ? 0 : span / N + 1;
+}
+
+extern "C" int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* row_scale,
+                                 float* out, int B, int T, int N, int K, ias_stream_t stream) {
+  IAS_REQUIRE(B > 0 && T > 0 && N > 0 && K > 0, IAS_ERR_INVALID, "ias_pqmf_analysis: B=%d T=%d N=%d K=%d", B, T, N, K);
+  IAS_REQUIRE(x && out, IAS_ERR_INVALID, "ias_pqmf_analysis: NULL pointer");
+  IAS_REQUIRE(H_dev || H_host, IAS_ERR_INVALID, "ias_pqmf_analysis: no filter given");
+  const int L = ias_pqmf_out_len(T, N, K);
+  IAS_REQUIRE(L > 0, IAS_ERR_INVALID, "ias_pqmf_analysis: empty output (T=%d K=%d)", T, K);
+  cudaStream_t st = as_stream(stream);
+  if (H_host && K == 63) {
+    switch (N) {
+      case 2: return launch_analysis<2, 63, 8>(x, H_host, row_scale, out, B, T, L, st);
+      case 3: return launch_analysis<3, 63, 8>(x, H_host, row_scale, out, B, T, L, st);
+      case 4: return launch_analysis<4, 63, 8>(x, H_host, row_scale, out, B, T, L, st);
+      case 8: return launch_analysis<8, 63, 4>(x, H_host, row_scale, out, B, T, L, st);
+      case 16: return launch_analysis<16, 63, 2>(x, H_host, row_scale, out, B, T, L, st);
+      default: break;
+    }
+  }
+  IAS_REQUIRE(H_dev, IAS_ERR_UNSUPPORTED, "ias_pqmf_analysis: N=%d K=%d has no specialised kernel and H_dev is NULL", N,
+              K);
+  const size_t total = (size_t)B * N * L;
+  {
+    ProfScope prof_(K_PQMF_ANALYSIS, st);
+    k_pqmf_analysis_generic<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, H_dev, row_scale, out, B, T, N, K, L);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_analysis_generic");
+  return IAS_OK;
+}
+
+extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, float* y, int B, int L,
+                                  int N, int K, ias_stream_t stream) {
+  IAS_REQUIRE(B > 0 && L > 0 && N > 0 && K > 0, IAS_ERR_INVALID, "ias_pqmf_synthesis: B=%d L=%d N=%d K=%d", B, L, N, K);
+  IAS_REQUIRE(z && y, IAS_ERR_INVALID, "ias_pqmf_synthesis: NULL pointer");
+  IAS_REQUIRE(G_dev || G_host, IAS_ERR_INVALID, "ias_pqmf_synthesis: no filter given");
+  cudaStream_t st = as_stream(stream);
+  if (G_host && K == 63) {
+    switch (N) {
+      case 2: return launch_synthesis<2, 63, 8>(z, G_host, y, B, L, st);
+      case 3: return launch_synthesis<3, 63, 8>(z, G_host, y, B, L, st);
+      case 4: return launch_synthesis<4, 63, 8>(z, G_host, y, B, L, st);
+      case 8: return launch_synthesis<8, 63, 4>(z, G_host, y, B, L, st);
+      case 16: return launch_synthesis<16, 63, 2>(z, G_host, y, B, L, st);
+      default: break;
+    }
+  }
+  IAS_REQUIRE(G_dev, IAS_ERR_UNSUPPORTED, "ias_pqmf_synthesis: N=%d K=%d has no specialised kernel and G_dev is NULL",
+              N, K);
+  const size_t total = (size_t)B * L * N;
+  {
+    ProfScope prof_(K_PQMF_SYNTHESIS, st);
+    k_pqmf_synthesis_generic<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(z, G_dev, y, B, L, N, K);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_synthesis_generic");
+  return IAS_OK;
+}

@@ -1,0 +1,596 @@
+// VICReg loss for sm_100a: invariance / variance / covariance terms of vicreg.VICReg.loss (vicreg.py:35-58) and
+// off_diagonal (vicreg.py:73-76), over the gathered batch.
+//
+// Forward pipeline (all on the caller's stream, no host sync):
+//   k_colsum        column sums of x and y (deterministic two-level), sum (x-y)^2 over the local rows
+//   k_center_pack   subtract the column mean, split every element into tf32 hi + tf32 lo, and write the transposed
+//                   operand X_c^T [D][B] as ready-made 128x32 shared-memory tile images (K-major, 128-byte swizzle)
+//   k_gram_tc       tcgen05 Gram: per CTA one 128x128 tile of X_c^T X_c over one K-split; operands arrive by
+//                   cp.async.bulk (TMA 1-D bulk copy) through a 3-stage mbarrier ring, 3 tf32 MMAs per k-step
+//                   (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM), epilogue tcgen05.ld -> partial tile
+//   k_cov_reduce    sum the K-split partials; off-diagonal squares (x2 for tiles above the diagonal), diagonal out
+//   k_finalize      variance -> std hinge, covariance scale, the four scalars
+// The only dense contraction of the hot path is the Gram, so it is the only tensor-core kernel (north star).
+#include "ias_common.cuh"
+
+#include <stdint.h>
+
+namespace ias {
+namespace {
+
+constexpr int TILE = 128;        // Gram output tile (UMMA M = N = 128)
+constexpr int KBLK = 32;         // batch rows per K-block: 32 tf32 = 128 B = one swizzle row
+constexpr int TILE_FLOATS = TILE * KBLK;          // 4096 floats = 16 KiB per operand tile image
+constexpr int TILE_BYTES = TILE_FLOATS * 4;
+constexpr int STAGES = 3;
+constexpr int COLSUM_ROWS = 128;  // rows per k_colsum CTA
+constexpr int MAX_SPLITS = 64;
+
+struct Plan {
+  int B, D, DT, Dp, KB, ntiles, splits, P;
+  size_t off_partial, off_repr, off_mean, off_packed, off_gram, off_covp, off_diag, off_stats, total;
+};
+
+__host__ inline Plan make_plan(int B, int D) {
+  Plan p;
+  p.B = B;
+  p.D = D;
+  p.DT = (D + TILE - 1) / TILE;
+  p.Dp = p.DT * TILE;
+  p.KB = (B + KBLK - 1) / KBLK;
+  p.ntiles = p.DT * (p.DT + 1) / 2;
+  // enough K-splits to cover ~one wave of 148 SMs, at least 2 K-blocks per split
+  int want = (148 + 2 * p.ntiles - 1) / (2 * p.ntiles);
+  int max_by_k = (p.KB + 1) / 2;
+  p.splits = want < 1 ? 1 : want;
+  if (p.splits > max_by_k) p.splits = max_by_k < 1 ? 1 : max_by_k;
+  if (p.splits > MAX_SPLITS) p.splits = MAX_SPLITS;
+  p.P = (B + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  size_t o = 0;
+  auto take = [&](size_t nfloats) {
+    size_t r = o;
+    o += (nfloats + 255) / 256 * 256;  // 1 KiB granularity keeps every region 1024-byte aligned
+    return r;
+  };
+  p.off_partial = take((size_t)p.P * 2 * D);
+  p.off_repr = take((size_t)p.P);
+  p.off_mean = take((size_t)2 * D);
+  p.off_packed = take((size_t)2 * 2 * p.DT * p.KB * TILE_FLOATS);
+  p.off_gram = take((size_t)2 * p.ntiles * p.splits * TILE * TILE);
+  p.off_covp = take((size_t)2 * p.ntiles * TILE);
+  p.off_diag = take((size_t)2 * p.Dp);
+  p.off_stats = take((size_t)8 * p.Dp);
+  p.total = o;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_colsum: grid = P, block = 256.  partial[p][s][d] = sum over the CTA's rows; repr[p] = sum (x-y)^2 over local rows
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ x, const float* __restrict__ y, int B, int D,
+                                                int local_row0, int local_rows, float* __restrict__ partial,
+                                                float* __restrict__ repr) {
+  __shared__ float s_red[8];
+  const int r0 = blockIdx.x * COLSUM_ROWS;
+  const int r1 = min(r0 + COLSUM_ROWS, B);
+  float rp = 0.0f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float sx = 0.0f, sy = 0.0f;
+    for (int r = r0; r < r1; ++r) {
+      const float a = __ldg(x + (size_t)r * D + d), c = __ldg(y + (size_t)r * D + d);
+      sx += a;
+      sy += c;
+      if (r >= local_row0 && r < local_row0 + local_rows) {
+        const float e = a - c;
+        rp = fmaf(e, e, rp);
+      }
+    }
+    partial[((size_t)blockIdx.x * 2 + 0) * D + d] = sx;
+    partial[((size_t)blockIdx.x * 2 + 1) * D + d] = sy;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rp += __shfl_xor_sync(0xffffffffu, rp, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = rp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    repr[blockIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_center_pack: grid = (KB, 2), block = 256.  One K-block (32 batch rows) of one matrix -> DT tile images, hi and lo.
+// Tile image (K-major, SWIZZLE_128B): element (row d, k) at byte (d/8)*1024 + (d%8)*128 + (((k/4) ^ (d%8))*16) + (k%4)*4.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256) k_center_pack(const float* __restrict__ x, const float* __restrict__ y, int B,
+                                                     int D, int P, int DT, int KB, const float* __restrict__ partial,
+                                                     float* __restrict__ mean_out, float* __restrict__ packed) {
+  const int kb = blockIdx.x, s = blockIdx.y;
+  const float* src = s ? y : x;
+  const float invB = 1.0f / (float)B;
+  for (int d = threadIdx.x; d < DT * TILE; d += blockDim.x) {
+    float mean = 0.0f;
+    if (d < D) {
+      float t = 0.0f;
+      for (int p = 0; p < P; ++p) t += partial[((size_t)p * 2 + s) * D + d];
+      mean = t * invB;
+      if (kb == 0) mean_out[s * D + d] = mean;
+    }
+    const int dt = d / TILE, dl = d % TILE;
+    float* hi = packed + ((((size_t)s * 2 + 0) * DT + dt) * KB + kb) * TILE_FLOATS;
+    float* lo = packed + ((((size_t)s * 2 + 1) * DT + dt) * KB + kb) * TILE_FLOATS;
+    const int rowbase = (dl >> 3) * 256 + (dl & 7) * 32;  // in floats
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 h, l;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = kb * KBLK + c * 4 + e;
+        v[e] = (d < D && r < B) ? __ldg(src + (size_t)r * D + d) - mean : 0.0f;
+      }
+      h.x = to_tf32(v[0]); h.y = to_tf32(v[1]); h.z = to_tf32(v[2]); h.w = to_tf32(v[3]);
+      l.x = to_tf32(v[0] - h.x); l.y = to_tf32(v[1] - h.y); l.z = to_tf32(v[2] - h.z); l.w = to_tf32(v[3] - h.w);
+      const int chunk = (c ^ (dl & 7)) * 4;
+      *reinterpret_cast<float4*>(hi + rowbase + chunk) = h;
+      *reinterpret_cast<float4*>(lo + rowbase + chunk) = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, bulk copy, tcgen05
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a lost arrival traps (error surfaces at the next CUDA call) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(ignored)=1 <<16 | SBO = 1024 B (8 rows x 128 B) >>4 <<32 | version 1 <<46 | layout SWIZZLE_128B (2) <<61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = N = 128 (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t IDESC_TF32_128x128 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE >> 3) << 17) |
+                                        ((uint32_t)(TILE >> 4) << 24);
+
+struct GramSmem {
+  float tile[STAGES][4][TILE_FLOATS];  // [stage][A_hi, A_lo, B_hi, B_lo], each 16 KiB, 1024-byte aligned
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+// grid = 2 * ntiles * splits, block = 128 (warp 0 lane 0: bulk-copy producer, warp 1 lane 0: MMA issuer, all: epilogue)
+__global__ void __launch_bounds__(128, 1) k_gram_tc(const float* __restrict__ packed, float* __restrict__ gram_partial,
+                                                    int DT, int KB, int ntiles, int splits) {
+  extern __shared__ uint8_t smem_raw[];
+  GramSmem& sm = *reinterpret_cast<GramSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int u = blockIdx.x;
+  const int split = u % splits;
+  u /= splits;
+  const int t = u % ntiles;
+  const int s = u / ntiles;
+  int tm = 0, rem = t;  // upper-triangular tile index -> (tm, tn), tn >= tm
+  while (rem >= DT - tm) {
+    rem -= DT - tm;
+    ++tm;
+  }
+  const int tn = tm + rem;
+  const bool diag = (tm == tn);
+  const int kb0 = (int)((long long)KB * split / splits);
+  const int kb1 = (int)((long long)KB * (split + 1) / splits);
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&sm.full[i], 1);
+      mbar_init(&sm.empty[i], 1);
+    }
+    mbar_init(&sm.done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // one warp allocates 128 TMEM columns (128 lanes x 128 fp32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                 "n"(TILE)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  const size_t part_stride = (size_t)DT * KB * TILE_FLOATS;  // hi -> lo
+  const float* a_hi = packed + (((size_t)s * 2 + 0) * DT + tm) * KB * TILE_FLOATS;
+  const float* b_hi = packed + (((size_t)s * 2 + 0) * DT + tn) * KB * TILE_FLOATS;
+
+  if (warp == 0 && lane == 0) {
+    // ---- producer: one elected thread feeds the ring with 16 KiB bulk copies ----
+    for (int i = 0; i < nkb; ++i) {
+      const int st = i % STAGES;
+      if (i >= STAGES) mbar_wait(&sm.empty[st], ((i / STAGES) - 1) & 1);
+      const size_t koff = (size_t)(kb0 + i) * TILE_FLOATS;
+      mbar_expect_tx(&sm.full[st], diag ? 2 * TILE_BYTES : 4 * TILE_BYTES);
+      bulk_g2s(sm.tile[st][0], a_hi + koff, TILE_BYTES, &sm.full[st]);
+      bulk_g2s(sm.tile[st][1], a_hi + part_stride + koff, TILE_BYTES, &sm.full[st]);
+      if (!diag) {
+        bulk_g2s(sm.tile[st][2], b_hi + koff, TILE_BYTES, &sm.full[st]);
+        bulk_g2s(sm.tile[st][3], b_hi + part_stride + koff, TILE_BYTES, &sm.full[st]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer: a single thread drives the tensor core ----
+    for (int i = 0; i < nkb; ++i) {
+      const int st = i % STAGES;
+      mbar_wait(&sm.full[st], (i / STAGES) & 1);
+      tc_fence_after();
+      const uint32_t ah = smem_u32(sm.tile[st][0]), al = smem_u32(sm.tile[st][1]);
+      const uint32_t bh = diag ? ah : smem_u32(sm.tile[st][2]);
+      const uint32_t bl = diag ? al : smem_u32(sm.tile[st][3]);
+#pragma unroll
+      for (int k = 0; k < KBLK / 8; ++k) {  // UMMA_K = 8 for tf32 = 32 bytes along the swizzle row
+        const uint64_t dah = umma_desc_sw128(ah + 32 * k), dal = umma_desc_sw128(al + 32 * k);
+        const uint64_t dbh = umma_desc_sw128(bh + 32 * k), dbl = umma_desc_sw128(bl + 32 * k);
+        tc_mma_tf32(tmem, dah, dbh, IDESC_TF32_128x128, (i | k) != 0);
+        tc_mma_tf32(tmem, dah, dbl, IDESC_TF32_128x128, 1);
+        tc_mma_tf32(tmem, dal, dbh, IDESC_TF32_128x128, 1);
+      }
+      tc_commit(&sm.empty[st]);  // frees the smem slot once these MMAs have read it
+    }
+    tc_commit(&sm.done);  // accumulator complete
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers -> partial tile (row = TMEM lane = thread) ----
+  mbar_wait(&sm.done, 0);
+  tc_fence_after();
+  float* dst = gram_partial + ((((size_t)s * ntiles + t) * splits + split) * TILE + threadIdx.x) * TILE;
+#pragma unroll
+  for (int c0 = 0; c0 < TILE; c0 += 32) {
+    uint32_t r[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (nkb > 0) {
+#pragma unroll
+      for (int c = 0; c < 32; c += 4)
+        *reinterpret_cast<float4*>(dst + c0 + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
+                                                               __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dst + c0 + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TILE) : "memory");
+  }
+}
+
+// Plain CUDA-core Gram of the same packed operands' source (test hook): gram[D][D] = xc^T xc in fp32.
+__global__ void __launch_bounds__(256) k_gram_simt(const float* __restrict__ x, const float* __restrict__ mean, int B,
+                                                   int D, float* __restrict__ gram) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
+  float acc = 0.0f;
+  for (int r0 = 0; r0 < B; r0 += 16) {
+    const int r = r0 + ty;
+    const int ca = blockIdx.y * 16 + tx, cb = blockIdx.x * 16 + tx;
+    sa[ty][tx] = (r < B && ca < D) ? x[(size_t)r * D + ca] - mean[ca] : 0.0f;
+    sb[ty][tx] = (r < B && cb < D) ? x[(size_t)r * D + cb] - mean[cb] : 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(sa[k][ty], sb[k][tx], acc);
+    __syncthreads();
+  }
+  if (i < D && j < D) gram[(size_t)i * D + j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_cov_reduce: grid = 2 * ntiles * (TILE/16), block = 256: 16 rows x 128 cols of one tile.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cov_reduce(const float* __restrict__ gram_partial, int DT, int ntiles,
+                                                    int splits, int Dp, float* __restrict__ covp,
+                                                    float* __restrict__ diag_out, float* __restrict__ gram_full) {
+  __shared__ float s_red[8];
+  int u = blockIdx.x;
+  const int rb = u % (TILE / 16);
+  u /= (TILE / 16);
+  const int t = u % ntiles;
+  const int s = u / ntiles;
+  int tm = 0, rem = t;
+  while (rem >= DT - tm) {
+    rem -= DT - tm;
+    ++tm;
+  }
+  const int tn = tm + rem;
+  const float* base = gram_partial + (((size_t)s * ntiles + t) * splits) * TILE * TILE;
+  float sq = 0.0f;
+  for (int e = threadIdx.x; e < 16 * TILE; e += 256) {
+    const int r = rb * 16 + e / TILE, c = e % TILE;
+    float g = 0.0f;
+    for (int k = 0; k < splits; ++k) g += base[(size_t)k * TILE * TILE + (size_t)r * TILE + c];
+    const int gi = tm * TILE + r, gj = tn * TILE + c;
+    if (gi == gj)
+      diag_out[s * Dp + gi] = g;
+    else
+      sq = fmaf(g, g, sq);
+    if (gram_full) {
+      gram_full[((size_t)s * Dp + gi) * Dp + gj] = g;
+      gram_full[((size_t)s * Dp + gj) * Dp + gi] = g;
+    }
+  }
+  if (tm != tn) sq *= 2.0f;  // the mirrored tile below the diagonal
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.0f;
+    for (int w = 0; w < 8; ++w) tsum += s_red[w];
+    covp[blockIdx.x] = tsum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_finalize: one CTA.  stats[s][0][d] = std, used by the backward pass.
+// ------------------------------------------------------------------------------------------------------------
+struct FinalArgs {
+  const float* repr;   // [P]
+  const float* covp;   // [2 * ntiles * 8]
+  const float* diag;   // [2][Dp]
+  float* stats;        // [2][Dp] std
+  float* out4;
+  int P, ncovp_per_side, D, Dp, B, B_local, cfgB, embeddim;
+  float sim, stdc, covc;
+};
+
+__global__ void __launch_bounds__(256) k_finalize(FinalArgs a) {
+  float hinge[2] = {0.0f, 0.0f};
+  for (int d = threadIdx.x; d < a.D; d += 256) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const float var = a.diag[s * a.Dp + d] / (float)(a.B - 1);  // NaN for B == 1, as torch.var
+      const float sd = sqrtf(var + 0.0001f);
+      a.stats[s * a.Dp + d] = sd;
+      hinge[s] += fmaxf(1.0f - sd, 0.0f);
+    }
+  }
+  // cov_x and cov_y partials are summed separately, then divided by embeddim, then added (vicreg.py:49-51)
+  float covx = 0.0f, covy = 0.0f;
+  for (int i = threadIdx.x; i < a.ncovp_per_side; i += 256) {
+    covx += a.covp[i];
+    covy += a.covp[a.ncovp_per_side + i];
+  }
+  float rp = 0.0f;
+  for (int i = threadIdx.x; i < a.P; i += 256) rp += a.repr[i];
+  float v[5] = {hinge[0], hinge[1], covx, covy, rp};
+  __shared__ float s_all[5][8];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    float t = v[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) s_all[q][threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot[5];
+    for (int q = 0; q < 5; ++q) {
+      float t = 0.0f;
+      for (int w = 0; w < 8; ++w) t += s_all[q][w];
+      tot[q] = t;
+    }
+    const float repr_loss = tot[4] / ((float)a.B_local * (float)a.D);
+    const float std_loss = (tot[0] / (float)a.D) / 2.0f + (tot[1] / (float)a.D) / 2.0f;
+    const float n1 = (float)(a.cfgB - 1);
+    const float cov_loss = (tot[2] / (n1 * n1)) / (float)a.embeddim + (tot[3] / (n1 * n1)) / (float)a.embeddim;
+    a.out4[0] = a.sim * repr_loss + a.stdc * std_loss + a.covc * cov_loss;
+    a.out4[1] = repr_loss;
+    a.out4[2] = std_loss;
+    a.out4[3] = cov_loss;
+  }
+}
+
+int check_common(const float* x, int B, int D, void* ws, size_t ws_bytes, const char* who) {
+  IAS_REQUIRE(B > 0 && D > 0, IAS_ERR_INVALID, "%s: B=%d D=%d", who, B, D);
+  IAS_REQUIRE(x != nullptr, IAS_ERR_INVALID, "%s: NULL input", who);
+  IAS_REQUIRE(D <= 16384, IAS_ERR_UNSUPPORTED, "%s: D=%d > 16384", who, D);
+  const Plan p = make_plan(B, D);
+  IAS_REQUIRE(ws && ws_bytes >= p.total * sizeof(float), IAS_ERR_WORKSPACE, "%s: workspace %zu < %zu bytes", who,
+              ws_bytes, p.total * sizeof(float));
+  IAS_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023u) == 0, IAS_ERR_INVALID, "%s: workspace must be 1024-byte aligned",
+              who);
+  return IAS_OK;
+}
+
+int launch_gram(const Plan& p, float* w, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = (int)sizeof(GramSmem) + 1024;
+  if (!attr_set) {
+    IAS_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  {
+    ProfScope prof_(K_VICREG_GRAM_TC, st);
+    k_gram_tc<<<2 * p.ntiles * p.splits, 128, smem, st>>>(w + p.off_packed, w + p.off_gram, p.DT, p.KB, p.ntiles,
+                                                          p.splits);
+  }
+  IAS_LAUNCH_CHECK("k_gram_tc");
+  return IAS_OK;
+}
+
+int run_stats_and_gram(const float* x, const float* y, const Plan& p, int local_row0, int B_local, float* w,
+                       float* gram_full, cudaStream_t st) {
+  {
+    ProfScope prof_(K_VICREG_COLSUM, st);
+    k_colsum<<<p.P, 256, 0, st>>>(x, y, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr);
+  }
+  IAS_LAUNCH_CHECK("k_colsum");
+  {
+    ProfScope prof_(K_VICREG_PACK, st);
+    k_center_pack<<<dim3(p.KB, 2), 256, 0, st>>>(x, y, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
+                                                 w + p.off_packed);
+  }
+  IAS_LAUNCH_CHECK("k_center_pack");
+  int rc = launch_gram(p, w, st);
+  if (rc) return rc;
+  {
+    ProfScope prof_(K_VICREG_COV_REDUCE, st);
+    k_cov_reduce<<<2 * p.ntiles * (TILE / 16), 256, 0, st>>>(w + p.off_gram, p.DT, p.ntiles, p.splits, p.Dp,
+                                                             w + p.off_covp, w + p.off_diag, gram_full);
+  }
+  IAS_LAUNCH_CHECK("k_cov_reduce");
+  return IAS_OK;
+}
+
+}  // namespace
+}  // namespace ias
+
+using namespace ias;
+
+extern "C" size_t ias_vicreg_workspace_bytes(int B, int D) {
+  if (B <= 0 || D <= 0) return 0;
+  return make_plan(B, D).total * sizeof(float);
+}
+
+extern "C" int ias_vicreg_loss(const float* x, const float* y, int B, int local_row0, int B_local, int cfg_batch_size,
+                               int D, int embeddim, float sim_coeff, float std_coeff, float cov_coeff, float* out4,
+                               void* workspace, size_t workspace_bytes, ias_stream_t stream) {
+  int rc = check_common(x, B, D, workspace, workspace_bytes, "ias_vicreg_loss");
+  if (rc) return rc;
+  IAS_REQUIRE(y && out4, IAS_ERR_INVALID, "ias_vicreg_loss: NULL pointer");
+  IAS_REQUIRE(local_row0 >= 0 && B_local > 0 && local_row0 + B_local <= B, IAS_ERR_INVALID,
+              "ias_vicreg_loss: local rows [%d,%d) outside [0,%d)", local_row0, local_row0 + B_local, B);
+  IAS_REQUIRE(cfg_batch_size != 1 && embeddim > 0, IAS_ERR_INVALID, "ias_vicreg_loss: cfg_batch_size=%d embeddim=%d",
+              cfg_batch_size, embeddim);
+  const Plan p = make_plan(B, D);
+  float* w = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  rc = run_stats_and_gram(x, y, p, local_row0, B_local, w, nullptr, st);
+  if (rc) return rc;
+  FinalArgs a;
+  a.repr = w + p.off_repr;
+  a.covp = w + p.off_covp;
+  a.diag = w + p.off_diag;
+  a.stats = w + p.off_stats;
+  a.out4 = out4;
+  a.P = p.P;
+  a.ncovp_per_side = p.ntiles * (TILE / 16);
+  a.D = D; a.Dp = p.Dp; a.B = B; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
+  a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
+  {
+    ProfScope prof_(K_VICREG_FINALIZE, st);
+    k_finalize<<<1, 256, 0, st>>>(a);
+  }
+  IAS_LAUNCH_CHECK("k_finalize");
+  return IAS_OK;
+}
+
+extern "C" int ias_vicreg_gram_tc(const float* x, int B, int D, float* gram, void* workspace, size_t workspace_bytes,
+                                  ias_stream_t stream) {
+  int rc = check_common(x, B, D, workspace, workspace_bytes, "ias_vicreg_gram_tc");
+  if (rc) return rc;
+  IAS_REQUIRE(gram, IAS_ERR_INVALID, "ias_vicreg_gram_tc: NULL output");
+  IAS_REQUIRE(D % TILE == 0, IAS_ERR_UNSUPPORTED, "ias_vicreg_gram_tc: test hook needs D %% 128 == 0 (D=%d)", D);
+  const Plan p = make_plan(B, D);
+  float* w = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  // the hook runs x against itself; `gram` receives both (identical) sides, [2][D][D]
+  return run_stats_and_gram(x, x, p, 0, B, w, gram, st);
+}
+
+extern "C" int ias_vicreg_gram_reference(const float* x, int B, int D, float* gram, void* workspace,
+                                         size_t workspace_bytes, ias_stream_t stream) {
+  int rc = check_common(x, B, D, workspace, workspace_bytes, "ias_vicreg_gram_reference");
+  if (rc) return rc;
+  IAS_REQUIRE(gram, IAS_ERR_INVALID, "ias_vicreg_gram_reference: NULL output");
+  const Plan p = make_plan(B, D);
+  float* w = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  k_colsum<<<p.P, 256, 0, st>>>(x, x, p.B, p.D, 0, B, w + p.off_partial, w + p.off_repr);
+  IAS_LAUNCH_CHECK("k_colsum");
+  k_center_pack<<<dim3(p.KB, 2), 256, 0, st>>>(x, x, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
+                                               w + p.off_packed);
+  IAS_LAUNCH_CHECK("k_center_pack");
+  {
+    ProfScope prof_(K_VICREG_GRAM_SIMT, st);
+    k_gram_simt<<<dim3((D + 15) / 16, (D + 15) / 16), 256, 0, st>>>(x, w + p.off_mean, B, D, gram);
+  }
+  IAS_LAUNCH_CHECK("k_gram_simt");
+  return IAS_OK;
+}
+
+extern "C" int ias_vicreg_loss_backward(const float* x, const float* y, int B, int local_row0, int B_local,
+                                        int cfg_batch_size, int D, int embeddim, float sim_coeff, float std_coeff,
+                                        float cov_coeff, const float* gout4, float* gx, float* gy, void* workspace,
+                                        size_t workspace_bytes, ias_stream_t stream) {
+  (void)x; (void)y; (void)B; (void)local_row0; (void)B_local; (void)cfg_batch_size; (void)D; (void)embeddim;
+  (void)sim_coeff; (void)std_coeff; (void)cov_coeff; (void)gout4; (void)gx; (void)gy; (void)workspace;
+  (void)workspace_bytes; (void)stream;
+  return ias::set_err(IAS_ERR_UNSUPPORTED, "ias_vicreg_loss_backward: not implemented yet (SURVEY 8f row 1)");
+}

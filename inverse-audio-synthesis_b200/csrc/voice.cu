@@ -1,0 +1,517 @@
+// Voice render for sm_100a: seeded parameters -> control-rate signals -> audio.
+//
+// Replaces torchsynth.synth.Voice as the reference calls it (vicreg_audio_params.py:86-94,114;
+// audio_to_params.py:196-203,215,238-257).  Three kernels:
+//   k_seed_params   one thread per sound: torch-CPU-compatible MT19937 (first 78 outputs of seed = sound id)
+//   k_voice_control one CTA per voice: from_0to1, 6 ADSR, 2 LFO (fp64 phase scan), modulation matrix -> ctrl[B][5][C]
+//   k_voice_audio   one CTA per voice, 8 samples per thread per tile: linear upsample of the 5 control signals,
+//                   2 VCO pitch paths, fp64 block scan of the phase increments, oscillators, VCAs, noise, mix,
+//                   running peak, optional normalize_if_clipping pass.
+// HBM traffic per voice: 4T audio written (+4T noise read when the table is not L2 resident, +8T on the voices
+// that clip when normalize != 0); ctrl/scratch are 11*C floats (L2 resident).
+#include "ias_common.cuh"
+#include "voice_math.cuh"
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace ias {
+namespace {
+
+using namespace vm;
+
+// ------------------------------------------------------------------------------------------------------------
+// parameter names / orders (host)
+// ------------------------------------------------------------------------------------------------------------
+struct NameTable {
+  std::vector<std::string> reg;      // "module/param", registration order
+  std::vector<std::string> dotted;   // "module.torchparameters.param"
+  int sorted_index[NROWS];           // registration row -> position in sorted(named_parameters())
+  uint8_t reg_of_sorted[NROWS];      // inverse
+};
+
+const NameTable& names() {
+  static const NameTable t = [] {
+    NameTable n;
+    const char* adsr[5] = {"attack", "decay", "sustain", "release", "alpha"};
+    const char* lfo[8] = {"frequency", "mod_depth", "initial_phase", "sin", "tri", "saw", "rsaw", "sqr"};
+    const char* vco[4] = {"tuning", "mod_depth", "initial_phase", "shape"};
+    const char* mod_in[4] = {"adsr_1", "adsr_2", "lfo_1", "lfo_2"};
+    const char* mod_out[5] = {"vco_1_pitch", "vco_1_amp", "vco_2_pitch", "vco_2_amp", "noise_amp"};
+    auto push = [&](const std::string& m, const std::string& p) {
+      n.reg.push_back(m + "/" + p);
+      n.dotted.push_back(m + ".torchparameters." + p);
+    };
+    push("keyboard", "midi_f0");
+    push("keyboard", "duration");
+    for (const char* m : {"adsr_1", "adsr_2"}) for (auto p : adsr) push(m, p);
+    for (const char* m : {"lfo_1", "lfo_2"}) for (auto p : lfo) push(m, p);
+    for (const char* m : {"lfo_1_amp_adsr", "lfo_2_amp_adsr", "lfo_1_rate_adsr", "lfo_2_rate_adsr"})
+      for (auto p : adsr) push(m, p);
+    for (auto i : mod_in) for (auto o : mod_out) push("mod_matrix", std::string(i) + "->" + o);
+    for (int i = 0; i < 3; ++i) push("vco_1", vco[i]);
+    for (int i = 0; i < 4; ++i) push("vco_2", vco[i]);
+    for (const char* p : {"vco_1", "vco_2", "noise"}) push("mixer", p);
+    std::vector<int> order(NROWS);
+    for (int i = 0; i < NROWS; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return n.dotted[a] < n.dotted[b]; });
+    for (int s = 0; s < NROWS; ++s) {
+      n.sorted_index[order[s]] = s;
+      n.reg_of_sorted[s] = (uint8_t)order[s];
+    }
+    return n;
+  }();
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_seed_params
+// ------------------------------------------------------------------------------------------------------------
+struct SeedTable {
+  uint8_t reg_of_sorted[NROWS];
+  uint8_t frozen[NROWS];
+};
+
+__global__ void __launch_bounds__(128) k_seed_params(long long first_id, int B, SeedTable tab,
+                                                     float* __restrict__ params01, uint8_t* __restrict__ is_train) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  unsigned long long id = (unsigned long long)(first_id + i);
+  // MT19937 state after init_genrand(low 32 bits of the seed); only mt[0..78] and mt[397..474] feed outputs 0..77
+  uint32_t lo[NROWS + 1];
+  uint32_t hi[NROWS];
+  uint32_t s = (uint32_t)id;
+  lo[0] = s;
+  for (int j = 1; j <= 396 + NROWS; ++j) {
+    s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)j;
+    if (j <= NROWS) lo[j] = s;
+    if (j >= 397) hi[j - 397] = s;
+  }
+  for (int k = 0; k < NROWS; ++k) {
+    uint32_t y = (lo[k] & 0x80000000u) | (lo[k + 1] & 0x7fffffffu);
+    uint32_t v = hi[k] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    v ^= v >> 11;
+    v ^= (v << 7) & 0x9d2c5680u;
+    v ^= (v << 15) & 0xefc60000u;
+    v ^= v >> 18;
+    int row = tab.reg_of_sorted[k];
+    if (!tab.frozen[row]) params01[(size_t)row * B + i] = (float)(v & 0xffffffu) * (1.0f / 16777216.0f);
+  }
+  if (is_train) is_train[i] = ((id / 32ull) % 10ull) != 9ull;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one double per thread (NT threads), total returned to every thread
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_up_d(double v, int d) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(0xffffffffu, lo, d);
+  hi = __shfl_up_sync(0xffffffffu, hi, d);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    double o = shfl_up_d(v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_voice_control
+// ------------------------------------------------------------------------------------------------------------
+constexpr int CTRL_THREADS = 256;
+
+struct ControlShared {
+  float P[NROWS];
+  Adsr adsr[6];  // adsr_1, adsr_2, lfo_1_amp, lfo_2_amp, lfo_1_rate, lfo_2_rate
+  Lfo lfo[2];
+  ModMatrix mm;
+  double wsum[2][CTRL_THREADS / 32];
+};
+
+__global__ void __launch_bounds__(CTRL_THREADS)
+k_voice_control(const float* __restrict__ params01, int B, int C, float cr, float eps, RangeTable ranges,
+                float* __restrict__ ctrl, float* __restrict__ scratch, float* __restrict__ vconst) {
+  __shared__ ControlShared sh;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+
+  if (tid < NROWS) sh.P[tid] = from_0to1(params01[(size_t)tid * B + b], ranges.r[tid]);
+  __syncthreads();
+  if (tid < 6) {
+    const int base[6] = {ADSR1, ADSR2, LFO1_AMP, LFO2_AMP, LFO1_RATE, LFO2_RATE};
+    sh.adsr[tid] = adsr_setup(&sh.P[base[tid]], sh.P[KEY_DURATION], cr);
+  } else if (tid < 8) {
+    sh.lfo[tid - 6] = lfo_setup(&sh.P[tid == 6 ? LFO1 : LFO2]);
+  } else if (tid == 8) {
+    sh.mm = modmatrix_setup(&sh.P[MODM]);
+  } else if (tid == 9) {
+    voice_constants(sh.P, vconst + (size_t)b * VC_COUNT);
+  }
+  __syncthreads();
+
+  float* sc = scratch + (size_t)b * 6 * C;  // [6][C]: x1|arg1, x2|arg2, amp1, amp2, adsr_1, adsr_2
+  // Phase A: pointwise envelopes and LFO phase increments
+  for (int j = tid; j < C; j += CTRL_THREADS) {
+    float n = (float)j;
+    float rate1 = adsr_eval(sh.adsr[4], n, eps);
+    float rate2 = adsr_eval(sh.adsr[5], n, eps);
+    sc[0 * C + j] = lfo_increment(sh.lfo[0], rate1, cr);
+    sc[1 * C + j] = lfo_increment(sh.lfo[1], rate2, cr);
+    sc[2 * C + j] = adsr_eval(sh.adsr[2], n, eps);
+    sc[3 * C + j] = adsr_eval(sh.adsr[3], n, eps);
+    sc[4 * C + j] = adsr_eval(sh.adsr[0], n, eps);
+    sc[5 * C + j] = adsr_eval(sh.adsr[1], n, eps);
+  }
+  __syncthreads();
+
+  // Phase B: inclusive scan of the two increment rows, fp64 accumulate, fp32 round per element (torch CPU cumsum)
+  const int chunk = (C + CTRL_THREADS - 1) / CTRL_THREADS;
+  const int j0 = min(tid * chunk, C), j1 = min(j0 + chunk, C);
+  double tot[2] = {0.0, 0.0};
+  for (int j = j0; j < j1; ++j) {
+    tot[0] += (double)sc[0 * C + j];
+    tot[1] += (double)sc[1 * C + j];
+  }
+  double pre[2];
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    double inc = warp_incl_scan(tot[l], lane);
+    if (lane == 31) sh.wsum[l][warp] = inc;
+    pre[l] = inc - tot[l];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    double acc = pre[l];
+    for (int w = 0; w < warp; ++w) acc += sh.wsum[l][w];
+    const float phase0 = sh.lfo[l].initial_phase;
+    for (int j = j0; j < j1; ++j) {
+      acc += (double)sc[l * C + j];
+      sc[l * C + j] = add((float)acc, phase0);
+    }
+  }
+  __syncthreads();
+
+  // Phase C: LFO shapes, VCAs, modulation matrix
+  float* out = ctrl + (size_t)b * IAS_VOICE_NCONTROL * C;
+  for (int j = tid; j < C; j += CTRL_THREADS) {
+    float l1 = mul(lfo_shapes_mix(sh.lfo[0], sc[0 * C + j]), sc[2 * C + j]);
+    float l2 = mul(lfo_shapes_mix(sh.lfo[1], sc[1 * C + j]), sc[3 * C + j]);
+    float a1 = sc[4 * C + j], a2 = sc[5 * C + j];
+#pragma unroll
+    for (int o = 0; o < 5; ++o) out[o * C + j] = modmatrix_out(sh.mm, o, a1, a2, l1, l2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_voice_audio
+// ------------------------------------------------------------------------------------------------------------
+constexpr int AUD_THREADS = 128;
+constexpr int AUD_SPT = 8;  // samples per thread per tile
+constexpr int AUD_TILE = AUD_THREADS * AUD_SPT;
+constexpr int AUD_WARPS = AUD_THREADS / 32;
+
+struct AudioArgs {
+  const float* ctrl;    // [B][5][C]
+  const float* vconst;  // [B][16]
+  const float* noise;   // [R][T]
+  float* audio;         // [B][T]
+  float* peak;          // [B] or null
+  float* phase_dbg;     // [B][2][T] or null
+  int B, T, C, noise_rows;
+  float scale;          // float(C-1)/float(T-1)
+  float sr, rsr;
+  int normalize;
+};
+
+// control values of signal `sig` at points j, j+1, j+2 (clamped), for a thread whose 8 samples start in interval j
+struct Ctl3 {
+  float v0, v1, v2;
+};
+__device__ __forceinline__ Ctl3 load_ctl(const float* __restrict__ row, int j, int C) {
+  Ctl3 c;
+  c.v0 = __ldg(row + min(j, C - 1));
+  c.v1 = __ldg(row + min(j + 1, C - 1));
+  c.v2 = __ldg(row + min(j + 2, C - 1));
+  return c;
+}
+__device__ __forceinline__ float ctl_interp(const Ctl3& c, int d, float l0, float l1) {
+  // d = i0 - j in {0,1}; the clamped loads make x[i1] == x[i0] at the final control point, as torch does
+  return upsample_mix(d ? c.v1 : c.v0, d ? c.v2 : c.v1, l0, l1);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(AUD_THREADS, 6) k_voice_audio(AudioArgs A) {
+  __shared__ double s_wsum[2][2][AUD_WARPS];  // [buffer][vco][warp]
+  __shared__ float s_peak[AUD_WARPS];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = A.T, C = A.C;
+  const float* vc = A.vconst + (size_t)b * VC_COUNT;
+  const float midi1 = vc[VC_MIDI1], depth1 = vc[VC_DEPTH1], phase1 = vc[VC_PHASE1];
+  const float midi2 = vc[VC_MIDI2], depth2 = vc[VC_DEPTH2], phase2 = vc[VC_PHASE2];
+  const float pk = vc[VC_PK], shape = vc[VC_SHAPE], gain2 = vc[VC_GAIN2];
+  const float lev1 = vc[VC_LEVEL1], lev2 = vc[VC_LEVEL2], lev3 = vc[VC_LEVEL3];
+  const float* ctl = A.ctrl + (size_t)b * IAS_VOICE_NCONTROL * C;
+  const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
+  float* out = A.audio + (size_t)b * T;
+
+  double carry1 = 0.0, carry2 = 0.0;
+  float tpeak = 0.0f;
+  const int ntiles = (T + AUD_TILE - 1) / AUD_TILE;
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int t0 = tile * AUD_TILE + tid * AUD_SPT;
+    const int buf = tile & 1;
+    // ---- pass 1: phase increments of both VCOs -----------------------------------------------------------
+    int j;
+    {
+      int i1_;
+      float l0_, l1_;
+      upsample_coords(min(t0, T - 1), A.scale, C, j, i1_, l0_, l1_);
+    }
+    float x1[AUD_SPT], x2[AUD_SPT];
+    {
+      const Ctl3 p1 = load_ctl(ctl + 0 * C, j, C);
+      const Ctl3 p2 = load_ctl(ctl + 2 * C, j, C);
+#pragma unroll
+      for (int k = 0; k < AUD_SPT; ++k) {
+        int i0, i1;
+        float l0, l1;
+        upsample_coords(min(t0 + k, T - 1), A.scale, C, i0, i1, l0, l1);
+        const int d = i0 - j;
+        const float m1 = ctl_interp(p1, d, l0, l1);
+        const float m2 = ctl_interp(p2, d, l0, l1);
+        const bool live = (t0 + k) < T;
+        x1[k] = live ? vco_increment(midi1, depth1, m1, A.sr, A.rsr) : 0.0f;
+        x2[k] = live ? vco_increment(midi2, depth2, m2, A.sr, A.rsr) : 0.0f;
+      }
+    }
+    // ---- block scan (fp64; exact for 4 s clips) -----------------------------------------------
+    double tot1 = 0.0, tot2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < AUD_SPT; ++k) {
+      tot1 += (double)x1[k];
+      tot2 += (double)x2[k];
+    }
+    const double inc1 = warp_incl_scan(tot1, lane);
+    const double inc2 = warp_incl_scan(tot2, lane);
+    if (lane == 31) {
+      s_wsum[buf][0][warp] = inc1;
+      s_wsum[buf][1][warp] = inc2;
+    }
+    __syncthreads();
+    double acc1 = carry1 + (inc1 - tot1), acc2 = carry2 + (inc2 - tot2);
+#pragma unroll
+    for (int w = 0; w < AUD_WARPS; ++w) {
+      const double w1 = s_wsum[buf][0][w], w2 = s_wsum[buf][1][w];
+      if (w < warp) {
+        acc1 += w1;
+        acc2 += w2;
+      }
+      carry1 += w1;
+      carry2 += w2;
+    }
+    // ---- pass 2: oscillators, VCAs, noise, mix ------------------------------------------------------------------
+    float nzv[AUD_SPT];
+    if (VEC) {
+      if (t0 < T) {  // T % 8 == 0 on this path: whole groups only
+        const float4 n0 = __ldg(reinterpret_cast<const float4*>(nz + t0));
+        const float4 n1 = __ldg(reinterpret_cast<const float4*>(nz + t0 + 4));
+        nzv[0] = n0.x; nzv[1] = n0.y; nzv[2] = n0.z; nzv[3] = n0.w;
+        nzv[4] = n1.x; nzv[5] = n1.y; nzv[6] = n1.z; nzv[7] = n1.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < AUD_SPT; ++k) nzv[k] = 0.0f;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < AUD_SPT; ++k) nzv[k] = (t0 + k) < T ? __ldg(nz + t0 + k) : 0.0f;
+    }
+    const Ctl3 q1 = load_ctl(ctl + 1 * C, j, C);
+    const Ctl3 q2 = load_ctl(ctl + 3 * C, j, C);
+    const Ctl3 q3 = load_ctl(ctl + 4 * C, j, C);
+    float y[AUD_SPT];
+#pragma unroll
+    for (int k = 0; k < AUD_SPT; ++k) {
+      int i0, i1;
+      float l0, l1;
+      upsample_coords(min(t0 + k, T - 1), A.scale, C, i0, i1, l0, l1);
+      const int d = i0 - j;
+      acc1 += (double)x1[k];
+      acc2 += (double)x2[k];
+      const float arg1 = add((float)acc1, phase1);
+      const float arg2 = add((float)acc2, phase2);
+      const float v1 = mul(cos_arg(arg1), ctl_interp(q1, d, l0, l1));
+      const float v2 = mul(squaresaw(arg2, pk, shape, gain2), ctl_interp(q2, d, l0, l1));
+      const float v3 = mul(nzv[k], ctl_interp(q3, d, l0, l1));
+      y[k] = mix3(lev1, v1, lev2, v2, lev3, v3);
+      if ((t0 + k) < T) {
+        tpeak = fmaxf(tpeak, fabsf(y[k]));
+        if (A.phase_dbg) {
+          A.phase_dbg[((size_t)b * 2 + 0) * T + t0 + k] = arg1;
+          A.phase_dbg[((size_t)b * 2 + 1) * T + t0 + k] = arg2;
+        }
+      }
+    }
+    if (VEC) {
+      if (t0 < T) {
+        reinterpret_cast<float4*>(out + t0)[0] = make_float4(y[0], y[1], y[2], y[3]);
+        reinterpret_cast<float4*>(out + t0)[1] = make_float4(y[4], y[5], y[6], y[7]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < AUD_SPT; ++k)
+        if ((t0 + k) < T) out[t0 + k] = y[k];
+    }
+  }
+
+  // ---- per-voice peak, normalize_if_clipping -------------------------------------------------------------------
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) tpeak = fmaxf(tpeak, __shfl_xor_sync(0xffffffffu, tpeak, d));
+  if (lane == 0) s_peak[warp] = tpeak;
+  __syncthreads();  // also orders this CTA's global stores before the re-read below
+  float pkv = s_peak[0];
+#pragma unroll
+  for (int w = 1; w < AUD_WARPS; ++w) pkv = fmaxf(pkv, s_peak[w]);
+  if (tid == 0 && A.peak) A.peak[b] = pkv;
+  if (A.normalize && pkv > 1.0f) {
+    if (VEC) {
+      float4* o4 = reinterpret_cast<float4*>(out);
+      for (int i = tid; i < T / 4; i += AUD_THREADS) {
+        float4 v = o4[i];
+        v.x = vm::div(v.x, pkv); v.y = vm::div(v.y, pkv); v.z = vm::div(v.z, pkv); v.w = vm::div(v.w, pkv);
+        o4[i] = v;
+      }
+    } else {
+      for (int i = tid; i < T; i += AUD_THREADS) out[i] = vm::div(out[i], pkv);
+    }
+  }
+}
+
+struct VoiceWorkspace {
+  float* ctrl;
+  float* scratch;
+  float* vconst;
+};
+
+size_t workspace_floats(int B, int C) {
+  return (size_t)B * IAS_VOICE_NCONTROL * C + (size_t)B * 6 * C + (size_t)B * VC_COUNT;
+}
+
+VoiceWorkspace carve(void* ws, int B, int C) {
+  VoiceWorkspace w;
+  w.ctrl = reinterpret_cast<float*>(ws);
+  w.scratch = w.ctrl + (size_t)B * IAS_VOICE_NCONTROL * C;
+  w.vconst = w.scratch + (size_t)B * 6 * C;
+  return w;
+}
+
+int launch_control(const float* params01, int B, int C, float cr, float eps, const VoiceWorkspace& w,
+                   cudaStream_t st) {
+  static const RangeTable ranges = make_range_table();
+  {
+    ProfScope prof_(K_VOICE_CONTROL, st);
+    k_voice_control<<<B, CTRL_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, w.ctrl, w.scratch, w.vconst);
+  }
+  IAS_LAUNCH_CHECK("k_voice_control");
+  return IAS_OK;
+}
+
+}  // namespace
+}  // namespace ias
+
+using namespace ias;
+
+extern "C" const char* ias_voice_param_name(int reg_index) {
+  if (reg_index < 0 || reg_index >= vm::NROWS) return nullptr;
+  return names().reg[reg_index].c_str();
+}
+
+extern "C" int ias_voice_sorted_index(int reg_index) {
+  if (reg_index < 0 || reg_index >= vm::NROWS) return -1;
+  return names().sorted_index[reg_index];
+}
+
+extern "C" int ias_voice_seed_params(int64_t first_sound_id, int B, const uint8_t* frozen78_host, float* params01,
+                                     uint8_t* is_train, ias_stream_t stream) {
+  IAS_REQUIRE(B > 0, IAS_ERR_INVALID, "ias_voice_seed_params: B=%d", B);
+  IAS_REQUIRE(params01 != nullptr, IAS_ERR_INVALID, "ias_voice_seed_params: params01 is NULL");
+  SeedTable tab;
+  for (int i = 0; i < vm::NROWS; ++i) {
+    tab.reg_of_sorted[i] = names().reg_of_sorted[i];
+    tab.frozen[i] = frozen78_host ? frozen78_host[i] : 0;
+  }
+  {
+    ProfScope prof_(K_SEED_PARAMS, as_stream(stream));
+    k_seed_params<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>((long long)first_sound_id, B, tab, params01,
+                                                                  is_train);
+  }
+  IAS_LAUNCH_CHECK("k_seed_params");
+  return IAS_OK;
+}
+
+extern "C" size_t ias_voice_workspace_bytes(int B, int T, int C) {
+  (void)T;
+  if (B <= 0 || C <= 0) return 0;
+  return workspace_floats(B, C) * sizeof(float);
+}
+
+extern "C" int ias_voice_control(const float* params01, int B, int C, float control_rate, float eps, float* ctrl,
+                                 void* workspace, size_t workspace_bytes, ias_stream_t stream) {
+  IAS_REQUIRE(B > 0 && C > 1, IAS_ERR_INVALID, "ias_voice_control: B=%d C=%d", B, C);
+  IAS_REQUIRE(params01 && ctrl, IAS_ERR_INVALID, "ias_voice_control: NULL pointer");
+  IAS_REQUIRE(workspace && workspace_bytes >= ias_voice_workspace_bytes(B, 0, C), IAS_ERR_WORKSPACE,
+              "ias_voice_control: workspace %zu < %zu bytes", workspace_bytes, ias_voice_workspace_bytes(B, 0, C));
+  VoiceWorkspace w = carve(workspace, B, C);
+  int rc = launch_control(params01, B, C, control_rate, eps, w, as_stream(stream));
+  if (rc) return rc;
+  IAS_CUDA(cudaMemcpyAsync(ctrl, w.ctrl, (size_t)B * IAS_VOICE_NCONTROL * C * sizeof(float),
+                           cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return IAS_OK;
+}
+
+extern "C" int ias_voice_render(const float* params01, const float* noise, int noise_rows, float* audio, float* peak,
+                                int B, int T, int C, float sample_rate, float control_rate, float eps, int normalize,
+                                const float* ctrl_in, float* phase_dbg, void* workspace, size_t workspace_bytes,
+                                ias_stream_t stream) {
+  IAS_REQUIRE(B > 0 && T > 1 && C > 1 && noise_rows > 0, IAS_ERR_INVALID, "ias_voice_render: B=%d T=%d C=%d R=%d", B,
+              T, C, noise_rows);
+  IAS_REQUIRE(T < (1 << 24), IAS_ERR_UNSUPPORTED, "ias_voice_render: T=%d exceeds 2^24 samples", T);
+  IAS_REQUIRE((long long)(T - 1) >= (long long)AUD_SPT * (C - 1), IAS_ERR_UNSUPPORTED,
+              "ias_voice_render: needs at least %d audio samples per control sample (T=%d C=%d)", AUD_SPT, T, C);
+  IAS_REQUIRE(params01 && noise && audio, IAS_ERR_INVALID, "ias_voice_render: NULL pointer");
+  IAS_REQUIRE(sample_rate > 0.f && control_rate > 0.f, IAS_ERR_INVALID, "ias_voice_render: rates must be positive");
+  IAS_REQUIRE(workspace && workspace_bytes >= ias_voice_workspace_bytes(B, T, C), IAS_ERR_WORKSPACE,
+              "ias_voice_render: workspace %zu < %zu bytes", workspace_bytes, ias_voice_workspace_bytes(B, T, C));
+  cudaStream_t st = as_stream(stream);
+  VoiceWorkspace w = carve(workspace, B, C);
+  int rc = launch_control(params01, B, C, control_rate, eps, w, st);
+  if (rc) return rc;
+  AudioArgs a;
+  a.ctrl = ctrl_in ? ctrl_in : w.ctrl;
+  a.vconst = w.vconst;
+  a.noise = noise;
+  a.audio = audio;
+  a.peak = peak;
+  a.phase_dbg = phase_dbg;
+  a.B = B; a.T = T; a.C = C; a.noise_rows = noise_rows;
+  a.scale = (float)(C - 1) / (float)(T - 1);
+  a.sr = sample_rate;
+  a.rsr = 1.0f / sample_rate;
+  a.normalize = normalize;
+  const bool vec = (T % 8 == 0) && ias_aligned16(noise) && ias_aligned16(audio);
+  {
+    ProfScope prof_(K_VOICE_AUDIO, st);
+    if (vec)
+      k_voice_audio<true><<<B, AUD_THREADS, 0, st>>>(a);
+    else
+      k_voice_audio<false><<<B, AUD_THREADS, 0, st>>>(a);
+  }
+  IAS_LAUNCH_CHECK("k_voice_audio");
+  return IAS_OK;
+}

@@ -1,0 +1,104 @@
+"""Drop-in for the reference's ``pqmf.PQMF`` (pqmf.py:9-55) running on ``libias_b200.so``.
+
+Same constructor, attributes, persistent buffers (``H[N,1,taps+1]``, ``G[1,N,taps+1]``, ``updown_filter[N,N,N]``
+-- so checkpoints with ``gram.H`` etc. load unchanged) and methods ``forward`` / ``analysis`` / ``synthesis``.
+The filter design is host-side one-off work (scipy, like the reference); the filtering itself is
+``ias_pqmf_analysis`` / ``ias_pqmf_synthesis``.  Callers: ``vicreg_audio_params.py:40``, ``audioembed.py:38``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from scipy import signal as sig
+from torch import nn
+
+from . import _lib
+
+
+def design_filters(N: int, taps: int, cutoff: float, beta: float) -> Tuple[np.ndarray, np.ndarray]:
+    """Cosine-modulated analysis/synthesis banks of the reference (pqmf.py:18-30), float64 [N, taps+1] each.
+
+    The modulation is centred on ``(taps-1)/2`` exactly as the reference does (its own TODO at pqmf.py:26 says the
+    textbook value would be ``taps/2``); parity with the reference's bands requires keeping that."""
+    prototype = sig.firwin(taps + 1, cutoff, window=("kaiser", beta))
+    k = np.arange(N)[:, None]
+    j = np.arange(taps + 1)[None, :]
+    theta = (2 * k + 1) * (np.pi / (2 * N)) * (j - ((taps - 1) / 2))
+    phase = ((-1.0) ** k) * np.pi / 4
+    return 2 * prototype * np.cos(theta + phase), 2 * prototype * np.cos(theta - phase)
+
+
+class PQMF(nn.Module):
+    def __init__(self, N: int = 4, taps: int = 62, cutoff: float = 0.15, beta: float = 9.0):
+        super().__init__()
+        self.N = N
+        self.taps = taps
+        self.cutoff = cutoff
+        self.beta = beta
+        H, G = design_filters(N, taps, cutoff, beta)
+        self.register_buffer("H", torch.from_numpy(H[:, None, :]).float())
+        self.register_buffer("G", torch.from_numpy(G[None, :, :]).float())
+        updown = torch.zeros((N, N, N)).float()
+        updown[torch.arange(N), torch.arange(N), 0] = 1.0
+        self.register_buffer("updown_filter", updown)  # unused by the kernels; kept for state-dict parity
+        self.pad_fn = nn.ConstantPad1d(taps // 2, 0.0)
+        self._host_cache = {}
+
+    def _taps(self, which: str) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(device [N,K] contiguous, host [N,K] contiguous) of buffer ``which``, host copy refreshed when it changes."""
+        buf = getattr(self, which)
+        key = (buf.data_ptr(), buf._version, buf.device)
+        hit = self._host_cache.get(which)
+        if hit is None or hit[0] != key:
+            dev = buf.reshape(self.N, -1).contiguous()
+            host = dev.detach().to("cpu", torch.float32).contiguous()
+            hit = (key, dev, host)
+            self._host_cache[which] = hit
+        return hit[1], hit[2]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.analysis(x)
+
+    def analysis(self, x: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [B,1,T] -> [B,N,L]  (pqmf.py:49-50).  ``row_scale`` [B] optionally scales each row on the fly."""
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"PQMF.analysis expects [B,1,T], got {tuple(x.shape)}")
+        _lib.require_cuda(x, "PQMF.analysis input")
+        if x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("PQMF.analysis has no backward: the synth output it filters carries no gradient")
+        x = x.detach().to(torch.float32).contiguous()
+        B, _, T = x.shape
+        dev, host = self._taps("H")
+        K = host.shape[1]
+        lib = _lib.lib()
+        L = lib.ias_pqmf_out_len(T, self.N, K)
+        if L <= 0:
+            raise ValueError(f"PQMF.analysis: input too short (T={T})")
+        out = torch.empty((B, self.N, L), dtype=torch.float32, device=x.device)
+        if row_scale is not None:
+            row_scale = row_scale.detach().to(torch.float32).contiguous()
+        rc = lib.ias_pqmf_analysis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(row_scale), _lib.ptr(out), B, T,
+                                   self.N, K, _lib.current_stream(x.device))
+        _lib.check(rc, "ias_pqmf_analysis")
+        return out
+
+    def synthesis(self, x: torch.Tensor) -> torch.Tensor:
+        """z [B,N,L] -> [B,1,L*N]  (pqmf.py:52-55)."""
+        if x.dim() != 3 or x.shape[1] != self.N:
+            raise ValueError(f"PQMF.synthesis expects [B,{self.N},L], got {tuple(x.shape)}")
+        _lib.require_cuda(x, "PQMF.synthesis input")
+        if x.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("PQMF.synthesis has no backward")
+        x = x.detach().to(torch.float32).contiguous()
+        B, _, L = x.shape
+        dev, host = self._taps("G")
+        K = host.shape[1]
+        out = torch.empty((B, 1, L * self.N), dtype=torch.float32, device=x.device)
+        rc = _lib.lib().ias_pqmf_synthesis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(out), B, L, self.N, K,
+                                           _lib.current_stream(x.device))
+        _lib.check(rc, "ias_pqmf_synthesis")
+        # conv1d(padding=taps//2) keeps L*N samples for even `taps` (the default) and drops the last one for odd
+        keep = L * self.N + 2 * (self.taps // 2) - self.taps
+        return out if keep == out.shape[2] else out[:, :, :keep]

@@ -59,6 +59,17 @@ def synthesis(z: np.ndarray, G: np.ndarray, N: int) -> np.ndarray:
     return np.einsum("bktj,kj->bt", win, G.astype(np.float64)).astype(np.float32)
 
 
+def analysis_conv1d(x, H, N: int):
+    """Same contraction through torch's CPU conv1d (the library call the reference makes, pqmf.py:49-50); used for the
+    CPU-baseline timing so the baseline is not handicapped by the float64 numpy restatement above."""
+    import torch
+    import torch.nn.functional as F
+
+    xt = torch.as_tensor(x).unsqueeze(1)
+    Ht = torch.as_tensor(H).unsqueeze(1)
+    return F.conv1d(xt, Ht, padding=(H.shape[1] - 1) // 2, stride=N)
+
+
 def rel_err(a: np.ndarray, b: np.ndarray) -> float:
     """The tolerance metric of SURVEY 8(c): max|a-b| / max|b|."""
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) / max(np.max(np.abs(b)), 1e-30))

@@ -56,6 +56,27 @@ def loss(
     return float(total), float(repr_loss), float(std_loss), float(cov_loss)
 
 
+def loss_torch(x, y, cfg_batch_size: int, embeddim: int, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0):
+    """The same terms with torch CPU fp32 ops in the reference's order (vicreg.py:35-58); CPU-baseline timing path."""
+    import torch
+    import torch.nn.functional as F
+
+    repr_loss = F.mse_loss(x, y)
+    x = x - x.mean(dim=0)
+    y = y - y.mean(dim=0)
+    std_x = torch.sqrt(x.var(dim=0) + 0.0001)
+    std_y = torch.sqrt(y.var(dim=0) + 0.0001)
+    std_loss = torch.mean(F.relu(1 - std_x)) / 2 + torch.mean(F.relu(1 - std_y)) / 2
+    cov_x = (x.T @ x) / (cfg_batch_size - 1)
+    cov_y = (y.T @ y) / (cfg_batch_size - 1)
+    n = cov_x.shape[0]
+    offx = cov_x.flatten()[:-1].view(n - 1, n + 1)[:, 1:]
+    offy = cov_y.flatten()[:-1].view(n - 1, n + 1)[:, 1:]
+    cov_loss = offx.pow(2).sum() / embeddim + offy.pow(2).sum() / embeddim
+    total = sim_coeff * repr_loss + std_coeff * std_loss + cov_coeff * cov_loss
+    return float(total), float(repr_loss), float(std_loss), float(cov_loss)
+
+
 def loss_grad(x, y, cfg_batch_size, embeddim, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0):
     """Analytic d loss / d x, d loss / d y in float64 (single process, all rows local)."""
     x = x.astype(np.float64)

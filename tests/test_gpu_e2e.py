@@ -1,0 +1,55 @@
+"""GPU: the whole front end (Voice -> PQMF -> bridge -> VICReg loss) through the public API against the CPU oracle."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import harness
+
+pytestmark = pytest.mark.gpu
+
+
+def test_front_end_step_vs_oracle(cuda_device):
+    import ias_b200
+
+    B = 64
+    cfg = ias_b200.SynthConfig(batch_size=B, reproducible=True, sample_rate=44100, buffer_size_seconds=4.0)
+    voice = ias_b200.Voice(synthconfig=cfg).to(cuda_device)
+    gram = ias_b200.PQMF(N=3).to(cuda_device)
+    vcfg = types.SimpleNamespace(dim=256, embeddim=256, vicreg=types.SimpleNamespace(
+        mlp="8-8-%d", batch_size=B, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
+    vic = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity())
+    wa, wp = harness.bridge_weights(cuda_device)
+    audio, params, is_train = voice(0)
+    bands = gram(audio.unsqueeze(1))
+    assert bands.shape == (B, 3, 58800)
+    x, y = harness.bridge(bands, params, wa, wp)
+    with torch.no_grad():
+        out = vic.loss(x, y)
+    got = np.array([float(o) for o in out])
+    ref = harness.oracle_front_end(0, B, N=3)
+    want = np.array(ref["loss4"])
+    rel = np.abs(got - want) / np.abs(want)
+    print("front end loss terms", got, want, rel)
+    # bands: the few voices whose audio differs (ill-conditioned pitch path) move the pooled features slightly
+    band_err = float((bands.cpu() - ref["bands"]).abs().max() / ref["bands"].abs().max())
+    print("bands rel err", band_err, "embedding rel err",
+          float((x.cpu() - ref["x"]).abs().max() / ref["x"].abs().max()))
+    assert np.all(rel <= 1e-3)
+    # loss on the ORACLE embeddings isolates the loss kernels: north-star tolerance
+    with torch.no_grad():
+        out2 = vic.loss(ref["x"].to(cuda_device), ref["y"].to(cuda_device))
+    got2 = np.array([float(o) for o in out2])
+    assert np.all(np.abs(got2 - want) <= 1e-4 * np.abs(want))
+    # PQMF on the ORACLE audio isolates the filter kernel
+    bands2 = gram(ref["audio"].unsqueeze(1).to(cuda_device))
+    assert float((bands2.cpu() - ref["bands"]).abs().max() / ref["bands"].abs().max()) <= 1e-5
+    # the image view the reference's AudioEmbedding takes (audioembed.py:41) is a pure reshape of the bands
+    assert bands.reshape(-1, 3, 240, 245).shape == (B, 3, 240, 245)
+
+
+def test_smoke_entry(cuda_device):
+    import __graft_entry__ as g
+
+    g.smoke()

@@ -1,0 +1,144 @@
+"""GPU parity: PQMF kernels (through the ias_b200.PQMF binding -> C ABI) against the oracle and the reference goldens.
+Tolerance (north star): max|a-b| / max|b| <= 1e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import make_golden as MG
+from oracle import pqmf as OP
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def cases():
+    return np.load(os.path.join(GOLDEN, "pqmf_cases.npz"))
+
+
+def _mod(N, cutoff, dev, **kw):
+    import ias_b200
+
+    return ias_b200.PQMF(N=N, cutoff=cutoff, **kw).to(dev)
+
+
+@pytest.mark.parametrize("name,N,cutoff,B,T", MG.PQMF_CASES)
+def test_analysis_and_synthesis_vs_reference_goldens(cuda_device, cases, name, N, cutoff, B, T):
+    m = _mod(N, cutoff, cuda_device)
+    x = MG.pqmf_input(B, T).to(cuda_device)
+    z = m(x)
+    ref_z = cases[f"{name}_analysis"]
+    assert tuple(z.shape) == ref_z.shape
+    assert OP.rel_err(z.cpu().numpy(), ref_z) <= TOL
+    y = m.synthesis(torch.from_numpy(ref_z).to(cuda_device))
+    ref_y = cases[f"{name}_synthesis"]
+    assert tuple(y.shape) == ref_y.shape
+    assert OP.rel_err(y.cpu().numpy(), ref_y) <= TOL
+    # and against the oracle restatement on the same seeded input
+    H, G = OP.design(N, cutoff=cutoff)
+    assert OP.rel_err(z.cpu().numpy(), OP.analysis(x.cpu().numpy()[:, 0, :], H, N)) <= TOL
+
+
+@pytest.mark.parametrize("name,N", [("n3_full", 3), ("n16_full", 16)])
+def test_full_length_vs_reference_subsample(cuda_device, cases, name, N):
+    m = _mod(N, 0.15, cuda_device)
+    x = MG.pqmf_input(2, 176400).to(cuda_device)
+    z = m.analysis(x)
+    assert z.shape == (2, N, (176400 - 1) // N + 1)
+    assert OP.rel_err(z[:, :, ::MG.SUB].cpu().numpy(), cases[f"{name}_analysis_sub"]) <= TOL
+    assert np.allclose(z.double().sum(dim=2).cpu().numpy(), cases[f"{name}_analysis_sum"], rtol=0, atol=5e-3)
+    assert np.allclose(z.double().abs().sum(dim=2).cpu().numpy(), cases[f"{name}_analysis_abssum"], rtol=1e-6)
+    y = m.synthesis(z)
+    assert y.shape == (2, 1, 176400)
+    # the golden synthesis ran on the reference's own analysis output; ours differs from that by <= 1e-5 relative
+    assert OP.rel_err(y[:, :, ::MG.SUB].cpu().numpy(), cases[f"{name}_synthesis_sub"]) <= 5 * TOL
+    assert np.allclose(y.double().abs().sum(dim=2).cpu().numpy(), cases[f"{name}_synthesis_abssum"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("N,taps", [(5, 62), (3, 30), (7, 41), (4, 63)])
+def test_generic_shapes_vs_oracle(cuda_device, N, taps):
+    """Shapes without a specialised kernel (any N, any tap count, even K) take the generic path."""
+    import ias_b200
+
+    m = ias_b200.PQMF(N=N, taps=taps).to(cuda_device)
+    H = m.H[:, 0, :].cpu().numpy()
+    G = m.G[0].cpu().numpy()
+    x = MG.pqmf_input(2, 3001, seed=3).to(cuda_device)
+    z = m(x)
+    K = taps + 1
+    if K % 2 == 1:  # the numpy oracle covers odd K (the reference's default); even K is checked by a direct sum
+        assert OP.rel_err(z.cpu().numpy(), OP.analysis(x.cpu().numpy()[:, 0, :], H, N)) <= TOL
+        y = m.synthesis(z)
+        assert OP.rel_err(y.cpu().numpy()[:, 0, :], OP.synthesis(z.cpu().numpy(), G, N)) <= TOL
+    else:
+        ref = torch.nn.functional.conv1d(x.cpu().double(), m.H.cpu().double(), padding=taps // 2, stride=N)
+        assert tuple(z.shape) == tuple(ref.shape)
+        assert OP.rel_err(z.cpu().numpy(), ref.float().numpy()) <= TOL
+
+
+def test_baseline_size_properties(cuda_device):
+    """Config 3 size (1024 x 4 s, N = 16 and 3): size-independent properties + oracle on a row subset."""
+    B, T = 1024, 176400
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = (torch.rand((B, 1, T), generator=g) * 2 - 1).to(cuda_device)
+    for N in (16, 3):
+        m = _mod(N, 0.15, cuda_device)
+        z = m(x)
+        # rows are independent: a row filtered alone is bit-identical to the same row inside the batch
+        for r in (0, 517, 1023):
+            assert torch.equal(m(x[r:r + 1]), z[r:r + 1])
+        # linearity
+        a, b2 = 0.75, -1.5
+        z2 = m(a * x[:8] + b2 * x[8:16])
+        lin = a * z[:8] + b2 * z[8:16]
+        assert float((z2 - lin).abs().max() / lin.abs().max()) <= TOL
+        # row_scale folds a per-row gain in (normalize_if_clipping folded into the consumer)
+        s = torch.rand(B, device=cuda_device) + 0.5
+        zs = m.analysis(x, row_scale=s)
+        assert float((zs - z * s[:, None, None]).abs().max() / z.abs().max()) <= TOL
+        # oracle on two rows, and the reference's own reconstruction behaviour (not small!)
+        H, G = OP.design(N)
+        rows = [3, 1000]
+        assert OP.rel_err(z[rows].cpu().numpy(), OP.analysis(x[rows, 0].cpu().numpy(), H, N)) <= TOL
+        y = m.synthesis(z)
+        assert y.shape == (B, 1, T)
+        assert OP.rel_err(y[rows, 0].cpu().numpy(), OP.synthesis(z[rows].cpu().numpy(), G, N)) <= TOL
+
+
+def test_long_clip_and_ragged_lengths(cuda_device):
+    m = _mod(16, 0.15, cuda_device)
+    x = MG.pqmf_input(2, 1323000, seed=5).to(cuda_device)  # 30 s
+    z = m(x)
+    assert z.shape == (2, 16, 82688)
+    y = m.synthesis(z)
+    assert y.shape == (2, 1, 1323008)
+    H, G = OP.design(16)
+    assert OP.rel_err(z[:1].cpu().numpy(), OP.analysis(x[:1, 0].cpu().numpy(), H, 16)) <= TOL
+    assert OP.rel_err(y[:1, 0].cpu().numpy(), OP.synthesis(z[:1].cpu().numpy(), G, 16)) <= TOL
+    m3 = _mod(3, 0.15, cuda_device)
+    for T in (1, 2, 31, 32, 62, 63, 64, 95, 1025, 3073, 6145):
+        xs = MG.pqmf_input(3, T, seed=T).to(cuda_device)
+        zs = m3(xs)
+        H3, G3 = OP.design(3)
+        ref = OP.analysis(xs[:, 0].cpu().numpy(), H3, 3)
+        assert zs.shape == ref.shape
+        assert np.abs(zs.cpu().numpy() - ref).max() <= TOL * max(np.abs(ref).max(), 1e-3)
+        ys = m3.synthesis(zs)
+        refy = OP.synthesis(zs.cpu().numpy(), G3, 3)
+        assert np.abs(ys[:, 0].cpu().numpy() - refy).max() <= TOL * max(np.abs(refy).max(), 1e-3)
+
+
+def test_checkpoint_loaded_filter_is_used(cuda_device):
+    """H/G are persistent buffers (state-dict keys gram.H ...): values loaded from a checkpoint must be the taps used."""
+    import ias_b200
+
+    m = ias_b200.PQMF(N=3).to(cuda_device)
+    x = MG.pqmf_input(1, 4096).to(cuda_device)
+    z0 = m(x)
+    sd = m.state_dict()
+    sd["H"] = sd["H"] * 2.0
+    m.load_state_dict(sd)
+    assert float((m(x) - 2 * z0).abs().max()) <= 1e-6 * float(z0.abs().max())
