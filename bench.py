@@ -301,7 +301,7 @@ def run_ours(args):
             "per_gpu_batch": B, "global_batch": B * world, "seconds": args.seconds, "bands": args.bands,
             "noise": "reproducible (32-row table)",
             "l2": "inputs larger than L2: 722 MB audio + 722 MB bands per step vs 126 MB L2",
-            "bridge": "torch abs + adaptive_avg_pool1d + 2 matmuls (harness, not a reference component), inside the step",
+            "bridge": "abs-mean pool to 256 bins (k_abs_avg_pool) + 2 torch matmuls (harness, not a reference component), inside the step",
         },
         "roofline": {
             "bound": "hbm", "kernel": "k_voice_audio", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -138,6 +138,11 @@ IAS_API int ias_vicreg_gram_reference(const float* x, int B, int D, float* gram,
 IAS_API int ias_vicreg_gram_tc(const float* x, int B, int D, float* gram, void* workspace, size_t workspace_bytes,
                        ias_stream_t stream);
 
+/* ---- Harness utility (not a reference surface) -------------------------------------------------------------
+ * out[b][i] = mean |x[b][j]| over torch's adaptive_avg_pool1d bin i of a length-S row, i < P.  Used by the benchmark's
+ * stand-in for the out-of-scope backbone between the PQMF bands and the embeddings (SURVEY.md 8d "harness bridge"). */
+IAS_API int ias_abs_avg_pool(const float* x, float* out, int B, long long S, int P, ias_stream_t stream);
+
 /* ---- Embedding all-gather: vicreg.FullGatherLayer (vicreg.py:79-95; intended call vicreg.py:38-39) ------- */
 
 /* These five live in libias_comm.so (links NCCL); ias_comm_last_error() is that library's error string. */

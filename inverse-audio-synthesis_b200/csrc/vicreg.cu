@@ -28,7 +28,7 @@ constexpr int MAX_SPLITS = 64;
 
 struct Plan {
   int B, D, DT, Dp, KB, ntiles, splits, P;
-  size_t off_partial, off_repr, off_mean, off_packed, off_gram, off_covp, off_diag, off_stats, total;
+  size_t off_partial, off_varpart, off_repr, off_mean, off_packed, off_gram, off_covp, off_diag, off_stats, total;
 };
 
 __host__ inline Plan make_plan(int B, int D) {
@@ -53,6 +53,7 @@ __host__ inline Plan make_plan(int B, int D) {
     return r;
   };
   p.off_partial = take((size_t)p.P * 2 * D);
+  p.off_varpart = take((size_t)p.P * 2 * D);
   p.off_repr = take((size_t)p.P);
   p.off_mean = take((size_t)2 * D);
   p.off_packed = take((size_t)2 * 2 * p.DT * p.KB * TILE_FLOATS);
@@ -109,10 +110,13 @@ __device__ __forceinline__ float to_tf32(float v) {
   return __uint_as_float(r);
 }
 
+constexpr int PACK_KB = COLSUM_ROWS / KBLK;  // K-blocks per k_center_pack CTA (same row blocking as k_colsum)
+
 __global__ void __launch_bounds__(256) k_center_pack(const float* __restrict__ x, const float* __restrict__ y, int B,
                                                      int D, int P, int DT, int KB, const float* __restrict__ partial,
-                                                     float* __restrict__ mean_out, float* __restrict__ packed) {
-  const int kb = blockIdx.x, s = blockIdx.y;
+                                                     float* __restrict__ mean_out, float* __restrict__ varpart,
+                                                     float* __restrict__ packed) {
+  const int pb = blockIdx.x, s = blockIdx.y;
   const float* src = s ? y : x;
   const float invB = 1.0f / (float)B;
   for (int d = threadIdx.x; d < DT * TILE; d += blockDim.x) {
@@ -121,27 +125,38 @@ __global__ void __launch_bounds__(256) k_center_pack(const float* __restrict__ x
       float t = 0.0f;
       for (int p = 0; p < P; ++p) t += partial[((size_t)p * 2 + s) * D + d];
       mean = t * invB;
-      if (kb == 0) mean_out[s * D + d] = mean;
+      if (pb == 0) mean_out[s * D + d] = mean;
     }
     const int dt = d / TILE, dl = d % TILE;
-    float* hi = packed + ((((size_t)s * 2 + 0) * DT + dt) * KB + kb) * TILE_FLOATS;
-    float* lo = packed + ((((size_t)s * 2 + 1) * DT + dt) * KB + kb) * TILE_FLOATS;
     const int rowbase = (dl >> 3) * 256 + (dl & 7) * 32;  // in floats
+    float sq4[PACK_KB];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float4 h, l;
-      float v[4];
+    for (int q = 0; q < PACK_KB; ++q) {
+      const int kb = pb * PACK_KB + q;
+      sq4[q] = 0.0f;
+      if (kb >= KB) continue;
+      float* hi = packed + ((((size_t)s * 2 + 0) * DT + dt) * KB + kb) * TILE_FLOATS;
+      float* lo = packed + ((((size_t)s * 2 + 1) * DT + dt) * KB + kb) * TILE_FLOATS;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = kb * KBLK + c * 4 + e;
-        v[e] = (d < D && r < B) ? __ldg(src + (size_t)r * D + d) - mean : 0.0f;
+      for (int c = 0; c < 8; ++c) {
+        float4 h, l;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = kb * KBLK + c * 4 + e;
+          v[e] = (d < D && r < B) ? __ldg(src + (size_t)r * D + d) - mean : 0.0f;
+          sq4[q] = fmaf(v[e], v[e], sq4[q]);
+        }
+        h.x = to_tf32(v[0]); h.y = to_tf32(v[1]); h.z = to_tf32(v[2]); h.w = to_tf32(v[3]);
+        l.x = to_tf32(v[0] - h.x); l.y = to_tf32(v[1] - h.y); l.z = to_tf32(v[2] - h.z); l.w = to_tf32(v[3] - h.w);
+        const int chunk = (c ^ (dl & 7)) * 4;
+        *reinterpret_cast<float4*>(hi + rowbase + chunk) = h;
+        *reinterpret_cast<float4*>(lo + rowbase + chunk) = l;
       }
-      h.x = to_tf32(v[0]); h.y = to_tf32(v[1]); h.z = to_tf32(v[2]); h.w = to_tf32(v[3]);
-      l.x = to_tf32(v[0] - h.x); l.y = to_tf32(v[1] - h.y); l.z = to_tf32(v[2] - h.z); l.w = to_tf32(v[3] - h.w);
-      const int chunk = (c ^ (dl & 7)) * 4;
-      *reinterpret_cast<float4*>(hi + rowbase + chunk) = h;
-      *reinterpret_cast<float4*>(lo + rowbase + chunk) = l;
     }
+    // centred second moment of this CTA's 128 rows (fp32, two-level); the variance comes from these, not from the
+    // Gram diagonal: the hinge 1 - std amplifies a relative error of the variance by ~1/(1 - std)
+    if (d < D) varpart[((size_t)pb * 2 + s) * D + d] = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
   }
 }
 
@@ -159,7 +174,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // Bounded wait: a lost arrival traps (error surfaces at the next CUDA call) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(256) k_cov_reduce(const float* __restrict__ gr
       sq = fmaf(g, g, sq);
     if (gram_full) {
       gram_full[((size_t)s * Dp + gi) * Dp + gj] = g;
-      gram_full[((size_t)s * Dp + gj) * Dp + gi] = g;
+      if (tm != tn) gram_full[((size_t)s * Dp + gj) * Dp + gi] = g;  // tiles below the diagonal are never computed
     }
   }
   if (tm != tn) sq *= 2.0f;  // the mirrored tile below the diagonal
@@ -402,7 +417,7 @@ __global__ void __launch_bounds__(256) k_cov_reduce(const float* __restrict__ gr
 struct FinalArgs {
   const float* repr;   // [P]
   const float* covp;   // [2 * ntiles * 8]
-  const float* diag;   // [2][Dp]
+  const float* varpart;  // [P][2][D] centred second-moment partials
   float* stats;        // [2][Dp] std
   float* out4;
   int P, ncovp_per_side, D, Dp, B, B_local, cfgB, embeddim;
@@ -414,7 +429,9 @@ __global__ void __launch_bounds__(256) k_finalize(FinalArgs a) {
   for (int d = threadIdx.x; d < a.D; d += 256) {
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      const float var = a.diag[s * a.Dp + d] / (float)(a.B - 1);  // NaN for B == 1, as torch.var
+      float ss = 0.0f;
+      for (int p = 0; p < a.P; ++p) ss += a.varpart[((size_t)p * 2 + s) * a.D + d];
+      const float var = ss / (float)(a.B - 1);  // NaN for B == 1, as torch.var
       const float sd = sqrtf(var + 0.0001f);
       a.stats[s * a.Dp + d] = sd;
       hinge[s] += fmaxf(1.0f - sd, 0.0f);
@@ -493,8 +510,8 @@ int run_stats_and_gram(const float* x, const float* y, const Plan& p, int local_
   IAS_LAUNCH_CHECK("k_colsum");
   {
     ProfScope prof_(K_VICREG_PACK, st);
-    k_center_pack<<<dim3(p.KB, 2), 256, 0, st>>>(x, y, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
-                                                 w + p.off_packed);
+    k_center_pack<<<dim3(p.P, 2), 256, 0, st>>>(x, y, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
+                                                w + p.off_varpart, w + p.off_packed);
   }
   IAS_LAUNCH_CHECK("k_center_pack");
   int rc = launch_gram(p, w, st);
@@ -536,7 +553,7 @@ extern "C" int ias_vicreg_loss(const float* x, const float* y, int B, int local_
   FinalArgs a;
   a.repr = w + p.off_repr;
   a.covp = w + p.off_covp;
-  a.diag = w + p.off_diag;
+  a.varpart = w + p.off_varpart;
   a.stats = w + p.off_stats;
   a.out4 = out4;
   a.P = p.P;
@@ -574,8 +591,8 @@ extern "C" int ias_vicreg_gram_reference(const float* x, int B, int D, float* gr
   cudaStream_t st = as_stream(stream);
   k_colsum<<<p.P, 256, 0, st>>>(x, x, p.B, p.D, 0, B, w + p.off_partial, w + p.off_repr);
   IAS_LAUNCH_CHECK("k_colsum");
-  k_center_pack<<<dim3(p.KB, 2), 256, 0, st>>>(x, x, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
-                                               w + p.off_packed);
+  k_center_pack<<<dim3(p.P, 2), 256, 0, st>>>(x, x, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
+                                              w + p.off_varpart, w + p.off_packed);
   IAS_LAUNCH_CHECK("k_center_pack");
   {
     ProfScope prof_(K_VICREG_GRAM_SIMT, st);

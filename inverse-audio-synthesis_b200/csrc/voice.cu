@@ -240,13 +240,8 @@ __device__ __forceinline__ Ctl3 load_ctl(const float* __restrict__ row, int j, i
   c.v2 = __ldg(row + min(j + 2, C - 1));
   return c;
 }
-__device__ __forceinline__ float ctl_interp(const Ctl3& c, int d, float l0, float l1) {
-  // d = i0 - j in {0,1}; the clamped loads make x[i1] == x[i0] at the final control point, as torch does
-  return upsample_mix(d ? c.v1 : c.v0, d ? c.v2 : c.v1, l0, l1);
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(AUD_THREADS, 6) k_voice_audio(AudioArgs A) {
+template <bool VEC, bool DBG>
+__global__ void __launch_bounds__(AUD_THREADS, 7) k_voice_audio(AudioArgs A) {
   __shared__ double s_wsum[2][2][AUD_WARPS];  // [buffer][vco][warp]
   __shared__ float s_peak[AUD_WARPS];
   const int b = blockIdx.x;
@@ -260,33 +255,32 @@ __global__ void __launch_bounds__(AUD_THREADS, 6) k_voice_audio(AudioArgs A) {
   const float* ctl = A.ctrl + (size_t)b * IAS_VOICE_NCONTROL * C;
   const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
   float* out = A.audio + (size_t)b * T;
+  const float scale = A.scale;
 
   double carry1 = 0.0, carry2 = 0.0;
   float tpeak = 0.0f;
   const int ntiles = (T + AUD_TILE - 1) / AUD_TILE;
-  for (int tile = 0; tile < ntiles; ++tile) {
+  float ft0 = (float)(tid * AUD_SPT);  // float(index of the thread's first sample); exact, advanced by AUD_TILE per tile
+  for (int tile = 0; tile < ntiles; ++tile, ft0 += (float)AUD_TILE) {
     const int t0 = tile * AUD_TILE + tid * AUD_SPT;
     const int buf = tile & 1;
+    // control interval of the thread's first sample (its 8 samples touch intervals j and j+1 only)
+    const int j = min((int)mul(scale, fminf(ft0, (float)(T - 1))), C - 1);
+    const float fj = (float)j;
     // ---- pass 1: phase increments of both VCOs -----------------------------------------------------------
-    int j;
-    {
-      int i1_;
-      float l0_, l1_;
-      upsample_coords(min(t0, T - 1), A.scale, C, j, i1_, l0_, l1_);
-    }
     float x1[AUD_SPT], x2[AUD_SPT];
     {
       const Ctl3 p1 = load_ctl(ctl + 0 * C, j, C);
       const Ctl3 p2 = load_ctl(ctl + 2 * C, j, C);
 #pragma unroll
       for (int k = 0; k < AUD_SPT; ++k) {
-        int i0, i1;
         float l0, l1;
-        upsample_coords(min(t0 + k, T - 1), A.scale, C, i0, i1, l0, l1);
-        const int d = i0 - j;
-        const float m1 = ctl_interp(p1, d, l0, l1);
-        const float m2 = ctl_interp(p2, d, l0, l1);
-        const bool live = (t0 + k) < T;
+        const bool d = upsample_coords_f(ft0 + (float)k, scale, fj, l0, l1);
+        const float m1 = upsample_mix(d ? p1.v1 : p1.v0, d ? p1.v2 : p1.v1, l0, l1);
+        const float m2 = upsample_mix(d ? p2.v1 : p2.v0, d ? p2.v2 : p2.v1, l0, l1);
+        // VEC: T % 8 == 0, so a thread is wholly live or wholly past the end; dead threads sit after every live
+        // one in the last tile, and an inclusive scan never feeds later totals into earlier lanes -> no masking.
+        const bool live = VEC || (t0 + k) < T;
         x1[k] = live ? vco_increment(midi1, depth1, m1, A.sr, A.rsr) : 0.0f;
         x2[k] = live ? vco_increment(midi2, depth2, m2, A.sr, A.rsr) : 0.0f;
       }
@@ -304,19 +298,7 @@ __global__ void __launch_bounds__(AUD_THREADS, 6) k_voice_audio(AudioArgs A) {
       s_wsum[buf][0][warp] = inc1;
       s_wsum[buf][1][warp] = inc2;
     }
-    __syncthreads();
-    double acc1 = carry1 + (inc1 - tot1), acc2 = carry2 + (inc2 - tot2);
-#pragma unroll
-    for (int w = 0; w < AUD_WARPS; ++w) {
-      const double w1 = s_wsum[buf][0][w], w2 = s_wsum[buf][1][w];
-      if (w < warp) {
-        acc1 += w1;
-        acc2 += w2;
-      }
-      carry1 += w1;
-      carry2 += w2;
-    }
-    // ---- pass 2: oscillators, VCAs, noise, mix ------------------------------------------------------------------
+    // loads of pass 2 issued before the barrier so their latency overlaps it
     float nzv[AUD_SPT];
     if (VEC) {
       if (t0 < T) {  // T % 8 == 0 on this path: whole groups only
@@ -335,24 +317,35 @@ __global__ void __launch_bounds__(AUD_THREADS, 6) k_voice_audio(AudioArgs A) {
     const Ctl3 q1 = load_ctl(ctl + 1 * C, j, C);
     const Ctl3 q2 = load_ctl(ctl + 3 * C, j, C);
     const Ctl3 q3 = load_ctl(ctl + 4 * C, j, C);
+    __syncthreads();
+    double acc1 = carry1 + (inc1 - tot1), acc2 = carry2 + (inc2 - tot2);
+#pragma unroll
+    for (int w = 0; w < AUD_WARPS; ++w) {
+      const double w1 = s_wsum[buf][0][w], w2 = s_wsum[buf][1][w];
+      if (w < warp) {
+        acc1 += w1;
+        acc2 += w2;
+      }
+      carry1 += w1;
+      carry2 += w2;
+    }
+    // ---- pass 2: oscillators, VCAs, noise, mix ------------------------------------------------------------------
     float y[AUD_SPT];
 #pragma unroll
     for (int k = 0; k < AUD_SPT; ++k) {
-      int i0, i1;
       float l0, l1;
-      upsample_coords(min(t0 + k, T - 1), A.scale, C, i0, i1, l0, l1);
-      const int d = i0 - j;
+      const bool d = upsample_coords_f(ft0 + (float)k, scale, fj, l0, l1);
       acc1 += (double)x1[k];
       acc2 += (double)x2[k];
       const float arg1 = add((float)acc1, phase1);
       const float arg2 = add((float)acc2, phase2);
-      const float v1 = mul(cos_arg(arg1), ctl_interp(q1, d, l0, l1));
-      const float v2 = mul(squaresaw(arg2, pk, shape, gain2), ctl_interp(q2, d, l0, l1));
-      const float v3 = mul(nzv[k], ctl_interp(q3, d, l0, l1));
+      const float v1 = mul(cos_arg(arg1), upsample_mix(d ? q1.v1 : q1.v0, d ? q1.v2 : q1.v1, l0, l1));
+      const float v2 = mul(squaresaw(arg2, pk, shape, gain2), upsample_mix(d ? q2.v1 : q2.v0, d ? q2.v2 : q2.v1, l0, l1));
+      const float v3 = mul(nzv[k], upsample_mix(d ? q3.v1 : q3.v0, d ? q3.v2 : q3.v1, l0, l1));
       y[k] = mix3(lev1, v1, lev2, v2, lev3, v3);
-      if ((t0 + k) < T) {
-        tpeak = fmaxf(tpeak, fabsf(y[k]));
-        if (A.phase_dbg) {
+      if (VEC || (t0 + k) < T) tpeak = fmaxf(tpeak, fabsf(y[k]));
+      if (DBG) {
+        if ((t0 + k) < T) {
           A.phase_dbg[((size_t)b * 2 + 0) * T + t0 + k] = arg1;
           A.phase_dbg[((size_t)b * 2 + 1) * T + t0 + k] = arg2;
         }
@@ -382,12 +375,14 @@ __global__ void __launch_bounds__(AUD_THREADS, 6) k_voice_audio(AudioArgs A) {
   if (A.normalize && pkv > 1.0f) {
     if (VEC) {
       float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll 1
       for (int i = tid; i < T / 4; i += AUD_THREADS) {
         float4 v = o4[i];
         v.x = vm::div(v.x, pkv); v.y = vm::div(v.y, pkv); v.z = vm::div(v.z, pkv); v.w = vm::div(v.w, pkv);
         o4[i] = v;
       }
     } else {
+#pragma unroll 1
       for (int i = tid; i < T; i += AUD_THREADS) out[i] = vm::div(out[i], pkv);
     }
   }
@@ -507,10 +502,14 @@ extern "C" int ias_voice_render(const float* params01, const float* noise, int n
   const bool vec = (T % 8 == 0) && ias_aligned16(noise) && ias_aligned16(audio);
   {
     ProfScope prof_(K_VOICE_AUDIO, st);
-    if (vec)
-      k_voice_audio<true><<<B, AUD_THREADS, 0, st>>>(a);
+    if (vec && !phase_dbg)
+      k_voice_audio<true, false><<<B, AUD_THREADS, 0, st>>>(a);
+    else if (vec)
+      k_voice_audio<true, true><<<B, AUD_THREADS, 0, st>>>(a);
+    else if (!phase_dbg)
+      k_voice_audio<false, false><<<B, AUD_THREADS, 0, st>>>(a);
     else
-      k_voice_audio<false><<<B, AUD_THREADS, 0, st>>>(a);
+      k_voice_audio<false, true><<<B, AUD_THREADS, 0, st>>>(a);
   }
   IAS_LAUNCH_CHECK("k_voice_audio");
   return IAS_OK;

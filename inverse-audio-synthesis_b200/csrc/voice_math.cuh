@@ -397,7 +397,7 @@ IAS_HD float modmatrix_out(const ModMatrix& mm, int o, float a1, float a2, float
 // ---- per-voice constants handed from the control stage to the audio stage ------------------------------------
 enum VoiceConst {
   VC_MIDI1 = 0, VC_DEPTH1, VC_PHASE1, VC_MIDI2, VC_DEPTH2, VC_PHASE2,
-  VC_PK,      // pi * partials_constant
+  VC_PK,      // pi * partials_constant * 0.5 * 2*log2(e): tanh argument scale folded with tanh_from_scaled's
   VC_SHAPE, VC_GAIN2,  // shape, 1 - shape/2
   VC_LEVEL1, VC_LEVEL2, VC_LEVEL3,
   VC_COUNT = 16
@@ -416,7 +416,7 @@ IAS_HD void voice_constants(const float* P, float* vc) {
   vc[VC_PHASE2] = P[VCO2 + 2];
   float max_f0 = midi_to_hz(add(midi_f0, fmaxf(P[VCO2 + 1], 0.0f)));
   float partials = div(12000.0f, mul(max_f0, log10_cr(max_f0)));
-  vc[VC_PK] = mul(IAS_PI_F, partials);
+  vc[VC_PK] = mul(mul(mul(IAS_PI_F, partials), 0.5f), 2.88539008177792681472f);
   vc[VC_SHAPE] = P[VCO2 + 3];
   vc[VC_GAIN2] = sub(1.0f, mul(P[VCO2 + 3], 0.5f));
   vc[VC_LEVEL1] = P[MIX + 0];
@@ -438,6 +438,17 @@ IAS_HD void upsample_coords(int i, float scale, int C, int& i0, int& i1, float& 
 }
 IAS_HD float upsample_mix(float v0, float v1, float l0, float l1) { return fma(l0, v0, mul(l1, v1)); }
 
+// Same coordinates without int<->float conversions, for a thread whose samples all fall in control intervals j or
+// j+1: fi = float(i), fj = float(j).  Returns d = i0 - j (0 or 1) and the two weights.
+IAS_HD bool upsample_coords_f(float fi, float scale, float fj, float& l0, float& l1) {
+  const float src = mul(scale, fi);
+  const float fj1 = add(fj, 1.0f);
+  const bool d = src >= fj1;
+  l1 = sub(src, d ? fj1 : fj);  // in [0,1) by construction: j = floor(src) of the thread's first sample
+  l0 = sub(1.0f, l1);
+  return d;
+}
+
 // VCO phase increment of one audio sample: 2*pi*hz(clamp(midi + depth*mod, 0, 127)) / sample_rate
 IAS_HD float vco_increment(float midi, float depth, float mod, float sr, float rsr) {
   float m = fminf(fmaxf(add(midi, mul(depth, mod)), 0.0f), 127.0f);
@@ -457,39 +468,62 @@ IAS_HD void reduce_half_turns(float a, float& f, int& n) {
   f = add(sub(p, nf), fma(a, C2, e));
 }
 
+// sin(pi*f) for |f| <= 0.5625 (reduce_half_turns can overshoot 0.5 by the ulp of a/pi for 30 s clips): odd degree-9
+// polynomial, relative error <= 1.9e-7, so the zero crossings that SquareSawVCO amplifies through tanh stay
+// accurate in absolute terms.
+IAS_HD float sinpi_poly(float f) {
+  const float u = mul(f, f);
+  float p = 0.07634329050779343f;
+  p = fma(p, u, -0.59761643409729f);
+  p = fma(p, u, 2.5499696731567383f);
+  p = fma(p, u, -5.1677045822143555f);
+  p = fma(p, u, 3.141592502593994f);
+  return mul(p, f);
+}
+
+// cos(pi*f) for f in [-0.5, 0.5], absolute error ~5e-7 (amplitude path only): the SFU cosine on the device.
+IAS_HD float cospi_fast(float f) {
+#ifdef __CUDA_ARCH__
+  return __cosf(mul(f, IAS_PI_F));
+#else
+  return (float)cos(3.14159265358979323846 * (double)f);
+#endif
+}
+
+// tanh(z) given u = 2*log2(e)*z:  1 - 2 / (exp2(u) + 1), absolute error ~1.5e-7; saturates correctly for huge |u|.
+IAS_HD float tanh_from_scaled(float u) {
+#ifdef __CUDA_ARCH__
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(add(e, 1.0f)));
+  return fma(-2.0f, r, 1.0f);
+#else
+  return (float)tanh((double)u / 2.88539008177792681472);
+#endif
+}
+
 IAS_HD void sincos_arg(float a, float& s, float& c) {
   float f;
   int n;
   reduce_half_turns(a, f, n);
-#ifdef __CUDA_ARCH__
-  sincospif(f, &s, &c);
-#else
-  s = (float)sin(3.14159265358979323846 * (double)f);
-  c = (float)cos(3.14159265358979323846 * (double)f);
-#endif
-  int flip = (n & 1) << 31;
-  s = i2f(f2i(s) ^ flip);
-  c = i2f(f2i(c) ^ flip);
+  const int flip = (n & 1) << 31;
+  s = i2f(f2i(sinpi_poly(f)) ^ flip);
+  c = i2f(f2i(cospi_fast(f)) ^ flip);
 }
 
 IAS_HD float cos_arg(float a) {
   float f;
   int n;
   reduce_half_turns(a, f, n);
-#ifdef __CUDA_ARCH__
-  float c = cospif(f);
-#else
-  float c = (float)cos(3.14159265358979323846 * (double)f);
-#endif
-  return i2f(f2i(c) ^ ((n & 1) << 31));
+  return i2f(f2i(cospi_fast(f)) ^ ((n & 1) << 31));
 }
 
-// SquareSawVCO.oscillator: (1 - shape/2) * tanh(pi*k*sin(arg)/2) * (1 + shape*cos(arg))
+// SquareSawVCO.oscillator: (1 - shape/2) * tanh(pi*k*sin(arg)/2) * (1 + shape*cos(arg)); pk = VC_PK (pre-scaled)
 IAS_HD float squaresaw(float arg, float pk, float shape, float gain) {
   float s, c;
   sincos_arg(arg, s, c);
-  float sq = tanhf(mul(mul(pk, s), 0.5f));
-  return mul(mul(gain, sq), add(1.0f, mul(shape, c)));
+  float sq = tanh_from_scaled(mul(pk, s));
+  return mul(mul(gain, sq), fma(shape, c, 1.0f));
 }
 
 // AudioMixer matmul [1,3]x[3,T]: FMA chain in k order

@@ -76,6 +76,7 @@ _SIGNATURES = {
     ),
     "ias_vicreg_gram_reference": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ias_vicreg_gram_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ias_abs_avg_pool": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_longlong, c_int, c_void_p]),
 }
 
 _COMM_SIGNATURES = {

@@ -59,6 +59,11 @@ class FullGatherLayer(torch.autograd.Function):
         if world == 1:
             return (x,)
         x = x.contiguous()
+        from . import dist as ias_dist
+
+        comm = ias_dist.active()
+        if comm is not None and x.is_cuda:
+            return tuple(comm.all_gather(x).to(x.dtype).unbind(0))
         out = torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(out.view(-1), x.view(-1))
         return tuple(out.unbind(0))
@@ -68,9 +73,17 @@ class FullGatherLayer(torch.autograd.Function):
         if ctx.world == 1:
             return grads[0]
         stacked = torch.stack(grads).contiguous()
-        own = torch.empty_like(stacked[0])
-        dist.reduce_scatter_tensor(own.view(-1), stacked.view(-1))
-        return own
+        from . import dist as ias_dist
+
+        comm = ias_dist.active()
+        if comm is not None and stacked.is_cuda:
+            return comm.reduce_scatter(stacked).to(stacked.dtype)
+        if dist.get_backend() == "nccl":
+            own = torch.empty_like(stacked[0])
+            dist.reduce_scatter_tensor(own.view(-1), stacked.view(-1))
+            return own
+        dist.all_reduce(stacked)  # gloo has no reduce-scatter: the reference's all-reduce + slice (vicreg.py:92-95)
+        return stacked[ctx.rank]
 
 
 class _VicregLossFn(torch.autograd.Function):

@@ -53,3 +53,20 @@ def test_smoke_entry(cuda_device):
     import __graft_entry__ as g
 
     g.smoke()
+
+
+def test_bridge_pool_kernel_matches_torch(cuda_device):
+    """The harness pooling kernel == torch's adaptive_avg_pool1d(|x|) (bins overlap by one element when S % P != 0)."""
+    for B, N, L, P in [(8, 3, 58800, 256), (3, 16, 11025, 256), (2, 1, 1000, 7), (2, 2, 256, 256)]:
+        g = torch.Generator().manual_seed(L)
+        bands = (torch.rand((B, N, L), generator=g) * 2 - 1)
+        ref = torch.nn.functional.adaptive_avg_pool1d(bands.abs().reshape(B, 1, -1).double(), P).squeeze(1)
+        wa = torch.eye(P, device=cuda_device)
+        harness_dim = harness.EMBED_DIM
+        try:
+            harness.EMBED_DIM = P
+            x, _ = harness.bridge(bands.to(cuda_device), torch.zeros(B, 78, device=cuda_device), wa,
+                                  torch.zeros(78, P, device=cuda_device))
+        finally:
+            harness.EMBED_DIM = harness_dim
+        assert float((x.cpu().double() - ref).abs().max() / ref.abs().max()) <= 1e-6

@@ -57,7 +57,7 @@ def test_large_argument_sincos(voice_shim):
     s, c = torch.empty_like(x), torch.empty_like(x)
     voice_shim.shim_sincos_arg(P(x), P(s), P(c), ctypes.c_long(x.numel()))
     xs, xc = torch.sin(x.double()), torch.cos(x.double())
-    assert float((s.double() - xs).abs().max()) < 2e-7 and float((c.double() - xc).abs().max()) < 2e-7
+    assert float((s.double() - xs).abs().max()) < 3e-7 and float((c.double() - xc).abs().max()) < 3e-7
     # near the zero crossings of sin the error must stay tiny in absolute terms: SquareSawVCO feeds sin through
     # tanh with a gain of up to ~2500 (pi * partials / 2 for the lowest notes)
     near_zero = xs.abs() < 1e-2
