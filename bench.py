@@ -34,8 +34,8 @@ ALGO_BYTES_PER_SOUND = 12 * T_4S + 8 * D  # synth writes 4T, PQMF r
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=1024)
     ap.add_argument("--bands", type=int, default=3)
@@ -55,14 +55,16 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []  # (arrival wall-clock, csv line)
         self.proc = None
+        self.t_begin = None
+        self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -70,7 +72,18 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -81,7 +94,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        lo = (self.t_begin or 0.0)
+        hi = (self.t_end or 1e30) + 0.15  # a sample describes the ~100 ms before it arrives
+        rows = [r for t, r in self.rows if lo <= t <= hi] or [r for _, r in self.rows[-3:]]
+        for r in rows:
             f = [c.strip() for c in r.split(",")]
             if len(f) < 9:
                 continue
@@ -185,26 +201,29 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     total_steps = args.warmup + args.steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # ---- device-resident timing: `value` ----
     for i in range(args.warmup):
         step(i)
     sync()
+    if rank == 0:
+        sampler.wait_first_sample()
     lib.ias_prof_reset()
     lib.ias_prof_enable(1)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ev = []
+    sync()
+    sampler.mark_begin()
     e0.record()
     for i in range(args.warmup, total_steps):
         out = step(i)
     e1.record()
     sync()
-    clocks = sampler.stop() if rank == 0 else None
-    lib.ias_prof_enable(0)
+    sampler.mark_end()
     ms_total = e0.elapsed_time(e1)
     launches = int(lib.ias_prof_launches(-1))
+    lib.ias_prof_enable(0)
     kern = {}
     import ctypes
 
@@ -260,6 +279,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_params_ms = float(t.item())
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -100,9 +100,14 @@ IAS_API int ias_pqmf_out_len(int T, int N, int K);
 /* PQMF.analysis / forward (pqmf.py:46-50): out[b][k][n] = sum_j H[k][j] * x[b][n*N + j - (K-1)/2].
  * H is the module buffer H[:,0,:] = [N][K]; H_host is the same values in host memory (fast paths pass the taps
  * as kernel arguments); H_dev is used when H_host is NULL or the shape has no specialised kernel.
+ * proto_host[K] / mod_host[N][2N] (both host, both optional) are the cosine-modulated factorisation of H,
+ * H[k][j] == proto[j] * mod[k][j % 2N]: when the caller knows H is the filter PQMF.__init__ designs (pqmf.py:18-30)
+ * it passes them and the kernel runs the polyphase form (63 + 2N^2 instead of 63N multiply-adds per time step);
+ * with NULL the direct form is used, valid for any H (e.g. taps loaded from a checkpoint).
  * row_scale[B] (may be NULL) multiplies row b of x, so normalize_if_clipping can be folded in (scale = 1/peak). */
-IAS_API int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* row_scale, float* out,
-                      int B, int T, int N, int K, ias_stream_t stream);
+IAS_API int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
+                      const float* mod_host, const float* row_scale, float* out, int B, int T, int N, int K,
+                      ias_stream_t stream);
 
 /* PQMF.synthesis (pqmf.py:52-55): zero-stuff by N with gain N, then the N->1 FIR G = [N][K] (buffer G[0]).
  * y[b][t], t < L*N. */

@@ -12,6 +12,8 @@
 // HBM traffic: 4T read + 4T written per sound in each direction (algorithmic minimum).
 #include "ias_common.cuh"
 
+#include <type_traits>
+
 namespace ias {
 namespace {
 
@@ -22,15 +24,23 @@ struct Taps {
   float h[N * K];
 };
 
+// Cosine-modulated factorisation of the analysis bank (pqmf.py:21-30): H[k][j] = g[j] * c[k][j mod 2N] with
+// g[j] = (-1)^floor(j/2N) * 2*prototype[j] and c[k][r] = cos((2k+1)*pi/(2N) * (r - (taps-1)/2) + (-1)^k*pi/4).
+template <int N, int K>
+struct TapsCM {
+  float g[K];
+  float c[N * 2 * N];
+};
+
 __host__ __device__ constexpr int odd_stride(int s) { return (s & 1) ? s : s + 1; }
 
 // ------------------------------------------------------------------------------------------------------------
 // analysis: out[b][k][n] = sum_j H[k][j] * x[b][n*N + j - PAD]
 // ------------------------------------------------------------------------------------------------------------
-template <int N, int K, int Q>
+template <int N, int K, int Q, class TapsT>
 __global__ void __launch_bounds__(PQ_THREADS)
 k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale, float* __restrict__ out, int T, int L,
-                int tiles_per_row, Taps<N, K> taps) {
+                int tiles_per_row, TapsT taps) {
   constexpr int PAD = (K - 1) / 2;
   constexpr int S = Q * N;                 // input samples consumed per thread
   constexpr int SP = odd_stride(S);        // padded stride in shared memory
@@ -86,12 +96,33 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   for (int q = 0; q < Q; ++q)
 #pragma unroll
     for (int k = 0; k < N; ++k) acc[q][k] = 0.0f;
+  if constexpr (std::is_same<TapsT, Taps<N, K>>::value) {
+    // direct form: 63*N FMA per time step; valid for any H (e.g. loaded from a checkpoint)
 #pragma unroll
-  for (int j = 0; j < K; ++j)
+    for (int j = 0; j < K; ++j)
 #pragma unroll
-    for (int k = 0; k < N; ++k)
+      for (int k = 0; k < N; ++k)
 #pragma unroll
-      for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.h[k * K + j], w[q * N + j], acc[q][k]);
+        for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.h[k * K + j], w[q * N + j], acc[q][k]);
+  } else {
+    // polyphase form: fold the 63 taps into 2N partial sums shared by all bands (63 FMA per time step), then the
+    // N x 2N cosine modulation (2N*N FMA per time step): 63 + 2N^2 instead of 63N
+    float ps[Q][2 * N];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int r = 0; r < 2 * N; ++r) ps[q][r] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) ps[q][j % (2 * N)] = fmaf(taps.g[j], w[q * N + j], ps[q][j % (2 * N)]);
+#pragma unroll
+    for (int r = 0; r < 2 * N; ++r)
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.c[k * 2 * N + r], ps[q][r], acc[q][k]);
+  }
 
   const int n0 = n_tile + threadIdx.x * Q;
   float* ob = out + (size_t)b * N * L;
@@ -266,15 +297,21 @@ __global__ void k_pqmf_synthesis_generic(const float* __restrict__ z, const floa
 }
 
 template <int N, int K, int Q>
-int launch_analysis(const float* x, const float* H_host, const float* row_scale, float* out, int B, int T, int L,
-                    cudaStream_t st) {
-  Taps<N, K> taps;
-  for (int i = 0; i < N * K; ++i) taps.h[i] = H_host[i];
+int launch_analysis(const float* x, const float* H_host, const float* proto_host, const float* mod_host,
+                    const float* row_scale, float* out, int B, int T, int L, cudaStream_t st) {
   constexpr int TILE_N = PQ_THREADS * Q;
   const int tiles = (L + TILE_N - 1) / TILE_N;
-  {
-    ProfScope prof_(K_PQMF_ANALYSIS, st);
-    k_pqmf_analysis<N, K, Q><<<(unsigned)((size_t)B * tiles), PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps);
+  const unsigned grid = (unsigned)((size_t)B * tiles);
+  ProfScope prof_(K_PQMF_ANALYSIS, st);
+  if (proto_host && mod_host) {
+    TapsCM<N, K> taps;
+    for (int i = 0; i < K; ++i) taps.g[i] = proto_host[i];
+    for (int i = 0; i < N * 2 * N; ++i) taps.c[i] = mod_host[i];
+    k_pqmf_analysis<N, K, Q, TapsCM<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps);
+  } else {
+    Taps<N, K> taps;
+    for (int i = 0; i < N * K; ++i) taps.h[i] = H_host[i];
+    k_pqmf_analysis<N, K, Q, Taps<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps);
   }
   IAS_LAUNCH_CHECK("k_pqmf_analysis");
   return IAS_OK;
@@ -306,8 +343,9 @@ extern "C" int ias_pqmf_out_len(int T, int N, int K) {
   return span < 0 ? 0 : span / N + 1;
 }
 
-extern "C" int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* row_scale,
-                                 float* out, int B, int T, int N, int K, ias_stream_t stream) {
+extern "C" int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
+                                 const float* mod_host, const float* row_scale, float* out, int B, int T, int N,
+                                 int K, ias_stream_t stream) {
   IAS_REQUIRE(B > 0 && T > 0 && N > 0 && K > 0, IAS_ERR_INVALID, "ias_pqmf_analysis: B=%d T=%d N=%d K=%d", B, T, N, K);
   IAS_REQUIRE(x && out, IAS_ERR_INVALID, "ias_pqmf_analysis: NULL pointer");
   IAS_REQUIRE(H_dev || H_host, IAS_ERR_INVALID, "ias_pqmf_analysis: no filter given");
@@ -316,11 +354,11 @@ extern "C" int ias_pqmf_analysis(const float* x, const float* H_dev, const float
   cudaStream_t st = as_stream(stream);
   if (H_host && K == 63) {
     switch (N) {
-      case 2: return launch_analysis<2, 63, 8>(x, H_host, row_scale, out, B, T, L, st);
-      case 3: return launch_analysis<3, 63, 8>(x, H_host, row_scale, out, B, T, L, st);
-      case 4: return launch_analysis<4, 63, 8>(x, H_host, row_scale, out, B, T, L, st);
-      case 8: return launch_analysis<8, 63, 4>(x, H_host, row_scale, out, B, T, L, st);
-      case 16: return launch_analysis<16, 63, 2>(x, H_host, row_scale, out, B, T, L, st);
+      case 2: return launch_analysis<2, 63, 8>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
+      case 3: return launch_analysis<3, 63, 8>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
+      case 4: return launch_analysis<4, 63, 8>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
+      case 8: return launch_analysis<8, 63, 4>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
+      case 16: return launch_analysis<16, 63, 2>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
       default: break;
     }
   }

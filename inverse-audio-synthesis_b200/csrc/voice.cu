@@ -130,6 +130,7 @@ struct ControlShared {
   Lfo lfo[2];
   ModMatrix mm;
   double wsum[2][CTRL_THREADS / 32];
+  int last_nz[CTRL_THREADS / 32];
 };
 
 __global__ void __launch_bounds__(CTRL_THREADS)
@@ -199,12 +200,29 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
 
   // Phase C: LFO shapes, VCAs, modulation matrix
   float* out = ctrl + (size_t)b * IAS_VOICE_NCONTROL * C;
+  int last_nz = -1;  // last control point where any amplitude signal (vco_1_amp, vco_2_amp, noise_amp) is non-zero
   for (int j = tid; j < C; j += CTRL_THREADS) {
     float l1 = mul(lfo_shapes_mix(sh.lfo[0], sc[0 * C + j]), sc[2 * C + j]);
     float l2 = mul(lfo_shapes_mix(sh.lfo[1], sc[1 * C + j]), sc[3 * C + j]);
     float a1 = sc[4 * C + j], a2 = sc[5 * C + j];
+    float o5[5];
 #pragma unroll
-    for (int o = 0; o < 5; ++o) out[o * C + j] = modmatrix_out(sh.mm, o, a1, a2, l1, l2);
+    for (int o = 0; o < 5; ++o) {
+      o5[o] = modmatrix_out(sh.mm, o, a1, a2, l1, l2);
+      out[o * C + j] = o5[o];
+    }
+    if (o5[1] != 0.0f || o5[3] != 0.0f || o5[4] != 0.0f) last_nz = j;
+  }
+  // Envelopes end in exact zeros (pow(0, alpha) == 0 after the release): tell the audio stage where the silent tail
+  // starts so it can write zeros instead of rendering oscillators that are multiplied by 0.
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) last_nz = max(last_nz, __shfl_xor_sync(0xffffffffu, last_nz, d));
+  if (lane == 0) sh.last_nz[warp] = last_nz;
+  __syncthreads();
+  if (tid == 0) {
+    int m = -1;
+    for (int w = 0; w < CTRL_THREADS / 32; ++w) m = max(m, sh.last_nz[w]);
+    vconst[(size_t)b * VC_COUNT + VC_SILENT_FROM] = (float)(m + 1);
   }
 }
 
@@ -227,6 +245,7 @@ struct AudioArgs {
   float scale;          // float(C-1)/float(T-1)
   float sr, rsr;
   int normalize;
+  int ctrl_overridden;  // ctrl comes from the caller (parity hook): the silent-tail marker does not describe it
 };
 
 // control values of signal `sig` at points j, j+1, j+2 (clamped), for a thread whose 8 samples start in interval j
@@ -240,6 +259,14 @@ __device__ __forceinline__ Ctl3 load_ctl(const float* __restrict__ row, int j, i
   c.v2 = __ldg(row + min(j + 2, C - 1));
   return c;
 }
+__device__ __noinline__ int live_tiles(int T, float scale, float silent_from_f) {
+  const int all = (T + AUD_TILE - 1) / AUD_TILE;
+  const int silent_from = (int)fminf(silent_from_f, 1e9f);
+  for (int t = 0; t < all; ++t)
+    if ((int)mul(scale, (float)(t * AUD_TILE)) >= silent_from) return t;
+  return all;
+}
+
 template <bool VEC, bool DBG>
 __global__ void __launch_bounds__(AUD_THREADS, 7) k_voice_audio(AudioArgs A) {
   __shared__ double s_wsum[2][2][AUD_WARPS];  // [buffer][vco][warp]
@@ -256,10 +283,12 @@ __global__ void __launch_bounds__(AUD_THREADS, 7) k_voice_audio(AudioArgs A) {
   const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
   float* out = A.audio + (size_t)b * T;
   const float scale = A.scale;
+  // Samples whose control interval [i0, i0+1] lies wholly in the silent tail are exactly 0 (every VCA gain is 0):
+  // render only the tiles before the first tile that starts inside the tail, zero-fill the rest.
+  const int ntiles = live_tiles(T, scale, A.ctrl_overridden ? 1e30f : vc[VC_SILENT_FROM]);
 
   double carry1 = 0.0, carry2 = 0.0;
   float tpeak = 0.0f;
-  const int ntiles = (T + AUD_TILE - 1) / AUD_TILE;
   float ft0 = (float)(tid * AUD_SPT);  // float(index of the thread's first sample); exact, advanced by AUD_TILE per tile
   for (int tile = 0; tile < ntiles; ++tile, ft0 += (float)AUD_TILE) {
     const int t0 = tile * AUD_TILE + tid * AUD_SPT;
@@ -363,6 +392,22 @@ __global__ void __launch_bounds__(AUD_THREADS, 7) k_voice_audio(AudioArgs A) {
     }
   }
 
+  // ---- silent tail -----------------------------------------------------------------------------------------
+  if (ntiles * AUD_TILE < T) {
+    if (VEC) {
+      float4* o4 = reinterpret_cast<float4*>(out);
+      for (int i = ntiles * (AUD_TILE / 4) + tid; i < T / 4; i += AUD_THREADS) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int i = ntiles * AUD_TILE + tid; i < T; i += AUD_THREADS) out[i] = 0.0f;
+    }
+    if (DBG) {
+      for (int i = ntiles * AUD_TILE + tid; i < T; i += AUD_THREADS) {
+        A.phase_dbg[((size_t)b * 2 + 0) * T + i] = 0.0f;
+        A.phase_dbg[((size_t)b * 2 + 1) * T + i] = 0.0f;
+      }
+    }
+  }
+
   // ---- per-voice peak, normalize_if_clipping -------------------------------------------------------------------
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) tpeak = fmaxf(tpeak, __shfl_xor_sync(0xffffffffu, tpeak, d));
@@ -373,17 +418,32 @@ __global__ void __launch_bounds__(AUD_THREADS, 7) k_voice_audio(AudioArgs A) {
   for (int w = 1; w < AUD_WARPS; ++w) pkv = fmaxf(pkv, s_peak[w]);
   if (tid == 0 && A.peak) A.peak[b] = pkv;
   if (A.normalize && pkv > 1.0f) {
+    // x / peak, correctly rounded (Markstein step with r = RN(1/peak)); 4 independent 16-byte loads in flight per
+    // thread so this second pass over the row runs at memory speed instead of one round trip per iteration
+    const float rp = vm::div(1.0f, pkv);
     if (VEC) {
       float4* o4 = reinterpret_cast<float4*>(out);
-#pragma unroll 1
-      for (int i = tid; i < T / 4; i += AUD_THREADS) {
-        float4 v = o4[i];
-        v.x = vm::div(v.x, pkv); v.y = vm::div(v.y, pkv); v.z = vm::div(v.z, pkv); v.w = vm::div(v.w, pkv);
-        o4[i] = v;
+      const int n4 = T / 4;
+      constexpr int U = 4;
+      for (int base = 0; base < n4; base += U * AUD_THREADS) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * AUD_THREADS + tid;
+          if (i < n4) v[u] = o4[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * AUD_THREADS + tid;
+          if (i < n4) {
+            v[u].x = div_const(v[u].x, pkv, rp); v[u].y = div_const(v[u].y, pkv, rp);
+            v[u].z = div_const(v[u].z, pkv, rp); v[u].w = div_const(v[u].w, pkv, rp);
+            o4[i] = v[u];
+          }
+        }
       }
     } else {
-#pragma unroll 1
-      for (int i = tid; i < T; i += AUD_THREADS) out[i] = vm::div(out[i], pkv);
+      for (int i = tid; i < T; i += AUD_THREADS) out[i] = div_const(out[i], pkv, rp);
     }
   }
 }
@@ -499,6 +559,7 @@ extern "C" int ias_voice_render(const float* params01, const float* noise, int n
   a.sr = sample_rate;
   a.rsr = 1.0f / sample_rate;
   a.normalize = normalize;
+  a.ctrl_overridden = ctrl_in != nullptr;
   const bool vec = (T % 8 == 0) && ias_aligned16(noise) && ias_aligned16(audio);
   {
     ProfScope prof_(K_VOICE_AUDIO, st);

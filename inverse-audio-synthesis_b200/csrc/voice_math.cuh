@@ -400,6 +400,7 @@ enum VoiceConst {
   VC_PK,      // pi * partials_constant * 0.5 * 2*log2(e): tanh argument scale folded with tanh_from_scaled's
   VC_SHAPE, VC_GAIN2,  // shape, 1 - shape/2
   VC_LEVEL1, VC_LEVEL2, VC_LEVEL3,
+  VC_SILENT_FROM,  // control index from which all three amplitude signals are exactly 0 to the end (as float)
   VC_COUNT = 16
 };
 
@@ -423,6 +424,7 @@ IAS_HD void voice_constants(const float* P, float* vc) {
   vc[VC_LEVEL2] = P[MIX + 1];
   vc[VC_LEVEL3] = P[MIX + 2];
   for (int i = VC_LEVEL3 + 1; i < VC_COUNT; ++i) vc[i] = 0.0f;
+  vc[VC_SILENT_FROM] = 1e30f;  // filled in by the control stage once the signals are known
 }
 
 // ---- audio rate ----------------------------------------------------------------------------------------------

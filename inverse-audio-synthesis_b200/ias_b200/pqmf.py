@@ -30,6 +30,19 @@ def design_filters(N: int, taps: int, cutoff: float, beta: float) -> Tuple[np.nd
     return 2 * prototype * np.cos(theta + phase), 2 * prototype * np.cos(theta - phase)
 
 
+def cosine_modulation_factors(N: int, taps: int, cutoff: float, beta: float) -> Tuple[np.ndarray, np.ndarray]:
+    """(g[taps+1], c[N, 2N]) float32 with H[k, j] == g[j] * c[k, j % 2N] up to fp32 rounding: the cosine of
+    pqmf.py:21-30 has period 4N in the tap index and flips sign every 2N taps, so the sign goes into the prototype
+    and the bank collapses to 2N polyphase partial sums followed by an N x 2N modulation."""
+    prototype = sig.firwin(taps + 1, cutoff, window=("kaiser", beta))
+    j = np.arange(taps + 1)
+    g = 2.0 * prototype * np.where((j // (2 * N)) % 2 == 0, 1.0, -1.0)
+    k = np.arange(N)[:, None]
+    r = np.arange(2 * N)[None, :]
+    c = np.cos((2 * k + 1) * (np.pi / (2 * N)) * (r - ((taps - 1) / 2)) + ((-1.0) ** k) * np.pi / 4)
+    return g.astype(np.float32), c.astype(np.float32)
+
+
 class PQMF(nn.Module):
     def __init__(self, N: int = 4, taps: int = 62, cutoff: float = 0.15, beta: float = 9.0):
         super().__init__()
@@ -44,19 +57,28 @@ class PQMF(nn.Module):
         updown[torch.arange(N), torch.arange(N), 0] = 1.0
         self.register_buffer("updown_filter", updown)  # unused by the kernels; kept for state-dict parity
         self.pad_fn = nn.ConstantPad1d(taps // 2, 0.0)
+        self.polyphase = True  # use the cosine-modulated fast path when H is the designed filter
         self._host_cache = {}
 
-    def _taps(self, which: str) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(device [N,K] contiguous, host [N,K] contiguous) of buffer ``which``, host copy refreshed when it changes."""
+    def _taps(self, which: str):
+        """(device [N,K], host [N,K], polyphase factors or None) of buffer ``which``; refreshed when the buffer
+        changes.  The factors are offered to the kernel only while the buffer still holds exactly the filter this
+        module designs (a checkpoint may have loaded other taps: then the direct form runs)."""
         buf = getattr(self, which)
         key = (buf.data_ptr(), buf._version, buf.device)
         hit = self._host_cache.get(which)
         if hit is None or hit[0] != key:
             dev = buf.reshape(self.N, -1).contiguous()
             host = dev.detach().to("cpu", torch.float32).contiguous()
-            hit = (key, dev, host)
+            factors = None
+            if which == "H":
+                H, _ = design_filters(self.N, self.taps, self.cutoff, self.beta)
+                if torch.equal(host, torch.from_numpy(H).float()):
+                    g, c = cosine_modulation_factors(self.N, self.taps, self.cutoff, self.beta)
+                    factors = (torch.from_numpy(g).contiguous(), torch.from_numpy(c).contiguous())
+            hit = (key, dev, host, factors)
             self._host_cache[which] = hit
-        return hit[1], hit[2]
+        return hit[1], hit[2], hit[3]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.analysis(x)
@@ -70,7 +92,8 @@ class PQMF(nn.Module):
             raise NotImplementedError("PQMF.analysis has no backward: the synth output it filters carries no gradient")
         x = x.detach().to(torch.float32).contiguous()
         B, _, T = x.shape
-        dev, host = self._taps("H")
+        dev, host, factors = self._taps("H")
+        proto, mod = factors if (factors is not None and self.polyphase) else (None, None)
         K = host.shape[1]
         lib = _lib.lib()
         L = lib.ias_pqmf_out_len(T, self.N, K)
@@ -79,8 +102,9 @@ class PQMF(nn.Module):
         out = torch.empty((B, self.N, L), dtype=torch.float32, device=x.device)
         if row_scale is not None:
             row_scale = row_scale.detach().to(torch.float32).contiguous()
-        rc = lib.ias_pqmf_analysis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(row_scale), _lib.ptr(out), B, T,
-                                   self.N, K, _lib.current_stream(x.device))
+        rc = lib.ias_pqmf_analysis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto), _lib.ptr(mod),
+                                   _lib.ptr(row_scale), _lib.ptr(out), B, T, self.N, K,
+                                   _lib.current_stream(x.device))
         _lib.check(rc, "ias_pqmf_analysis")
         return out
 
@@ -93,7 +117,7 @@ class PQMF(nn.Module):
             raise NotImplementedError("PQMF.synthesis has no backward")
         x = x.detach().to(torch.float32).contiguous()
         B, _, L = x.shape
-        dev, host = self._taps("G")
+        dev, host, _ = self._taps("G")
         K = host.shape[1]
         out = torch.empty((B, 1, L * self.N), dtype=torch.float32, device=x.device)
         rc = _lib.lib().ias_pqmf_synthesis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(out), B, L, self.N, K,

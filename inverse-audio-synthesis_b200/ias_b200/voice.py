@@ -320,14 +320,22 @@ class Voice(nn.Module):
         return (idxs // BASE_REPRODUCIBLE_BATCH_SIZE) % 10 != 9
 
     # ---- storage plumbing ----------------------------------------------------------------------------------
+    def _param_list(self) -> List[ModuleParameter]:
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = [getattr(self, m).torchparameters[n] for (m, n) in self._rows]  # registration order == row order
+            self.__dict__["_plist"] = plist
+        return plist
+
     def _tie(self) -> None:
         """Make every ModuleParameter a view of its row of ``_store`` again (after .to(), load_state_dict, or a user
-        assigning ``parameter.data``); values the user put in the parameter win."""
+        assigning ``parameter.data``); values the user put in the parameter win.  The common case (nothing moved) is
+        78 pointer comparisons."""
         store = self._store
-        for (module_name, param_name), row in self._rows.items():
-            p = getattr(self, module_name).torchparameters[param_name]
-            view = store[row]
-            if p.data.data_ptr() != view.data_ptr() or p.data.device != store.device:
+        base, stride = store.data_ptr(), store.stride(0) * store.element_size()
+        for row, p in enumerate(self._param_list()):
+            if p.data_ptr() != base + row * stride:
+                view = store[row]
                 view.copy_(p.data.to(device=store.device, dtype=store.dtype))
                 p.data = view
 
@@ -369,17 +377,14 @@ class Voice(nn.Module):
         _lib.check(rc, "ias_voice_seed_params")
 
     def _frozen_rows(self) -> List[int]:
-        out = [0] * _lib.NPARAMS
-        for (module_name, param_name), row in self._rows.items():
-            if getattr(self, module_name).torchparameters[param_name].frozen:
-                out[row] = 1
-        return out
+        return [1 if p.frozen else 0 for p in self._param_list()]
 
     def output(self, return_peak: bool = False, phase_debug: Optional[torch.Tensor] = None,
-               ctrl_in: Optional[torch.Tensor] = None) -> torch.Tensor:
+               ctrl_in: Optional[torch.Tensor] = None, _tied: bool = False) -> torch.Tensor:
         """Voice.output(): render the current parameters to audio [B, T].  ``phase_debug`` / ``ctrl_in`` are the
         inspection hooks of ``ias_voice_render`` (parity tests only)."""
-        self._tie()
+        if not _tied:
+            self._tie()
         cfg = self.synthconfig
         _lib.require_cuda(self._store, "Voice parameters")
         noise = self.noise.noise
@@ -423,10 +428,11 @@ class Voice(nn.Module):
         ctx = torch.no_grad() if self.synthconfig.no_grad else torch.enable_grad()
         with ctx:
             if batch_idx is not None:
-                self.randomize(seed=int(batch_idx))
+                self.randomize(seed=int(batch_idx))  # ties the parameter views
                 is_train = self._is_train.bool()
             else:
+                self._tie()
                 is_train = None
-            params = self.params01()
-            audio = self.output()
+            params = self._store.t().contiguous()
+            audio = self.output(_tied=True)
         return audio, params, is_train

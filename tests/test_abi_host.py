@@ -43,7 +43,7 @@ def test_library_loads_and_reports_errors(built_lib):
     lib = ias_b200.lib()
     assert lib.ias_version() >= 100
     # argument validation happens before any CUDA call, so it is testable without a GPU
-    rc = lib.ias_pqmf_analysis(None, None, None, None, None, 0, 10, 3, 63, None)
+    rc = lib.ias_pqmf_analysis(None, None, None, None, None, None, None, 0, 10, 3, 63, None)
     assert rc == 1 and b"ias_pqmf_analysis" in lib.ias_last_error()
     rc = lib.ias_voice_render(None, None, 0, None, None, 1, 100, 10, 44100.0, 441.0, 1e-6, 1, None, None, None, 0, None)
     assert rc == 1
@@ -135,6 +135,17 @@ def test_pqmf_module_surface(built_lib):
         assert list(m.state_dict().keys()) == ["H", "G", "updown_filter"]
         assert float(m.updown_filter.sum()) == N and float(m.updown_filter[1, 1, 0]) == 1.0
     assert ias_b200.PQMF().N == 4
+    # the polyphase factorisation offered to the kernel reproduces H to fp32 rounding
+    from ias_b200.pqmf import cosine_modulation_factors, design_filters
+    for N in (2, 3, 4, 8, 16):
+        g, c = cosine_modulation_factors(N, 62, 0.15, 9.0)
+        H, _ = design_filters(N, 62, 0.15, 9.0)
+        rebuilt = g[None, :].astype(np.float64) * c[:, np.arange(63) % (2 * N)].astype(np.float64)
+        assert np.abs(rebuilt - H).max() <= 2e-7 * np.abs(H).max()
+    m = ias_b200.PQMF(N=3)
+    assert m._taps("H")[2] is not None
+    m.H.mul_(2.0)  # taps that are no longer the designed filter: only the direct form may run
+    assert m._taps("H")[2] is None
     with pytest.raises(ias_b200.IasError):
         ias_b200.PQMF(N=3)(torch.zeros(1, 1, 100))
     with pytest.raises(ValueError):

@@ -131,6 +131,20 @@ def test_long_clip_and_ragged_lengths(cuda_device):
         assert np.abs(ys[:, 0].cpu().numpy() - refy).max() <= TOL * max(np.abs(refy).max(), 1e-3)
 
 
+@pytest.mark.parametrize("N", [2, 3, 4, 8, 16])
+def test_polyphase_and_direct_forms_agree(cuda_device, N):
+    """Designed filter -> polyphase kernel; same taps with the fast path disabled -> direct kernel; both vs oracle."""
+    m = _mod(N, 0.15, cuda_device)
+    x = MG.pqmf_input(3, 20011, seed=N).to(cuda_device)
+    zp = m(x)
+    m.polyphase = False
+    zd = m(x)
+    H, _ = OP.design(N)
+    ref = OP.analysis(x[:, 0].cpu().numpy(), H, N)
+    assert OP.rel_err(zp.cpu().numpy(), ref) <= TOL and OP.rel_err(zd.cpu().numpy(), ref) <= TOL
+    assert OP.rel_err(zp.cpu().numpy(), zd.cpu().numpy()) <= 2e-6
+
+
 def test_checkpoint_loaded_filter_is_used(cuda_device):
     """H/G are persistent buffers (state-dict keys gram.H ...): values loaded from a checkpoint must be the taps used."""
     import ias_b200
