@@ -301,6 +301,13 @@ def run_ours(args):
     # 32-row L2-resident one in reproducible mode) x B sounds.
     voice_bytes = 4.0 * T * B
     achieved = voice_bytes / (va["ms_per_launch"] * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+    try:
+        if B == 1024 and T == T_4S:
+            traffic = json.load(open(os.path.join(harness.ROOT, "profiles", "traffic.json")))["k_voice_audio"][
+                "per_launch_bytes"]
+    except Exception:
+        pass
     line = {
         "metric": "4s@44.1kHz sounds/sec (synth->PQMF->VICReg)",
         "value": value,
@@ -325,7 +332,7 @@ def run_ours(args):
         },
         "roofline": {
             "bound": "hbm", "kernel": "k_voice_audio", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": voice_bytes,
             "ms_per_launch": va["ms_per_launch"],
             "note": "k_voice_audio is instruction-issue bound, not HBM bound (DESIGN.md); step-level fraction below",
