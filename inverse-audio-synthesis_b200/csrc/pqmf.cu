@@ -34,6 +34,76 @@ struct TapsCM {
 
 __host__ __device__ constexpr int odd_stride(int s) { return (s & 1) ? s : s + 1; }
 
+// Shared-memory layout of a staged signal row.  Thread t reads a sliding window that starts at linear index t*S, so
+// rows are stored in chunks of S floats at a padded pitch SP chosen to keep those reads bank-conflict free:
+//   S % 4 == 0: SP is a multiple of 4 with SP/4 odd -> 128-bit loads/stores, the 8 lanes of a quarter warp hit 8
+//               distinct 16-byte bank groups;  otherwise: SP odd, 32-bit accesses.
+template <int S>
+struct Pad {
+  static constexpr bool VEC = (S % 4 == 0);
+  static constexpr int SP = VEC ? ((((S / 4) & 1) == 1) ? S : S + 4) : odd_stride(S);
+  __host__ __device__ static constexpr int at(int i) { return (i / S) * SP + (i % S); }
+  __host__ __device__ static constexpr int floats(int span) { return (span / S + 2) * SP; }
+};
+
+// Stage `SPAN4` float4 groups of one row into shared memory: global index g0 + 4*i4 (g0 % 4 == 0), zero outside
+// [0, len), scaled by `gain`.
+template <int S, int SPAN4>
+__device__ __forceinline__ void stage_row(float* __restrict__ dst, const float* __restrict__ row, int g0, int len,
+                                          float gain, bool vec_ok) {
+  using P = Pad<S>;
+  constexpr int STEP = 4 * PQ_THREADS;
+  int q = (4 * (int)threadIdx.x) / S, r = (4 * (int)threadIdx.x) % S;
+  for (int i4 = threadIdx.x; i4 < SPAN4; i4 += PQ_THREADS) {
+    const int g = g0 + 4 * i4;
+    float4 v;
+    if (vec_ok && g >= 0 && g + 3 < len) {
+      v = __ldg(reinterpret_cast<const float4*>(row + g));
+    } else {
+      v.x = (g + 0 >= 0 && g + 0 < len) ? __ldg(row + g + 0) : 0.0f;
+      v.y = (g + 1 >= 0 && g + 1 < len) ? __ldg(row + g + 1) : 0.0f;
+      v.z = (g + 2 >= 0 && g + 2 < len) ? __ldg(row + g + 2) : 0.0f;
+      v.w = (g + 3 >= 0 && g + 3 < len) ? __ldg(row + g + 3) : 0.0f;
+    }
+    v.x *= gain; v.y *= gain; v.z *= gain; v.w *= gain;
+    if constexpr (P::VEC) {
+      *reinterpret_cast<float4*>(dst + q * P::SP + r) = v;  // S % 4 == 0: a group never straddles a chunk
+      q += STEP / S;
+      r += STEP % S;
+      if (r >= S) {
+        r -= S;
+        ++q;
+      }
+    } else {
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[P::at(4 * i4 + c)] = e[c];
+    }
+  }
+}
+
+// Sliding window of this thread: linear floats [t*S + OFF, t*S + OFF + WIN) of the staged row -> registers.
+template <int S, int OFF, int WIN>
+__device__ __forceinline__ void load_window(const float* __restrict__ src, float (&w)[WIN]) {
+  using P = Pad<S>;
+  if constexpr (P::VEC) {
+    constexpr int G = (OFF + WIN + 3) / 4;
+    float4 g[G];
+    const float* base = src + threadIdx.x * P::SP;
+#pragma unroll
+    for (int i = 0; i < G; ++i) g[i] = *reinterpret_cast<const float4*>(base + P::at(4 * i));
+#pragma unroll
+    for (int c = 0; c < WIN; ++c) {
+      const float4 v = g[(OFF + c) / 4];
+      const int e = (OFF + c) % 4;
+      w[c] = e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w));
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < WIN; ++c) w[c] = src[P::at((int)threadIdx.x * S + OFF + c)];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // analysis: out[b][k][n] = sum_j H[k][j] * x[b][n*N + j - PAD]
 // ------------------------------------------------------------------------------------------------------------
@@ -43,54 +113,25 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
                 int tiles_per_row, TapsT taps) {
   constexpr int PAD = (K - 1) / 2;
   constexpr int S = Q * N;                 // input samples consumed per thread
-  constexpr int SP = odd_stride(S);        // padded stride in shared memory
   constexpr int WIN = (Q - 1) * N + K;     // input window of one thread
   constexpr int TILE_N = PQ_THREADS * Q;   // output steps per CTA
-  constexpr int SPAN = TILE_N * N + K - N + 4;  // staged samples (incl. up to 3 alignment samples, rounded)
+  static_assert((TILE_N * N) % 4 == 0, "tile start must keep 16-byte alignment");
+  constexpr int OFF = (4 - PAD % 4) % 4;   // staged window starts at a multiple of 4 <= first needed sample
+  constexpr int SPAN = TILE_N * N + K - N + 4;
   constexpr int SPAN4 = (SPAN + 3) / 4;
-  __shared__ float xs[(SPAN4 * 4 / S + 2) * SP];
+  __shared__ __align__(16) float xs[Pad<S>::floats(SPAN4 * 4)];
 
   const int b = blockIdx.x / tiles_per_row;
   const int tile = blockIdx.x - b * tiles_per_row;
   const int n_tile = tile * TILE_N;
-  const float* xr = x + (size_t)b * T;
   const float scale = row_scale ? row_scale[b] : 1.0f;
-
-  // staged window starts at g0 (multiple of 4, <= first needed sample)
-  const int first = n_tile * N - PAD;
-  const int off = ((first % 4) + 4) % 4;
-  const int g0 = first - off;
+  const int g0 = n_tile * N - PAD - OFF;  // multiple of 4
   const bool vec_ok = ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
-  for (int i4 = threadIdx.x; i4 < SPAN4; i4 += PQ_THREADS) {
-    const int g = g0 + 4 * i4;
-    float4 v;
-    if (vec_ok && g >= 0 && g + 3 < T) {
-      v = __ldg(reinterpret_cast<const float4*>(xr + g));
-    } else {
-      v.x = (g + 0 >= 0 && g + 0 < T) ? __ldg(xr + g + 0) : 0.0f;
-      v.y = (g + 1 >= 0 && g + 1 < T) ? __ldg(xr + g + 1) : 0.0f;
-      v.z = (g + 2 >= 0 && g + 2 < T) ? __ldg(xr + g + 2) : 0.0f;
-      v.w = (g + 3 >= 0 && g + 3 < T) ? __ldg(xr + g + 3) : 0.0f;
-    }
-    const float e[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int i = 4 * i4 + c;
-      xs[(i / S) * SP + (i % S)] = e[c];
-    }
-  }
+  stage_row<S, SPAN4>(xs, x + (size_t)b * T, g0, T, scale, vec_ok);
   __syncthreads();
 
-  // sliding window of this thread into registers
   float w[WIN];
-  {
-    const int base = threadIdx.x * S + off;  // tile-local index of x[n0*N - PAD]
-#pragma unroll
-    for (int c = 0; c < WIN; ++c) {
-      const int i = base + c;
-      w[c] = xs[(i / S) * SP + (i % S)];
-    }
-  }
+  load_window<S, OFF, WIN>(xs, w);
   float acc[Q][N];
 #pragma unroll
   for (int q = 0; q < Q; ++q)
@@ -192,42 +233,21 @@ k_pqmf_synthesis(const float* __restrict__ z, float* __restrict__ y, int L, int 
   using Geo = SynthGeom<N, K>;
   constexpr int DMIN = Geo::omin();
   constexpr int WIN = Q + Geo::omax() - DMIN;  // per-band window of one thread: n0+DMIN .. n0+Q-1+omax
-  constexpr int SP = odd_stride(Q);
   constexpr int TILE_N = PQ_THREADS * Q;
+  static_assert(TILE_N % 4 == 0, "tile start must keep 16-byte alignment");
+  constexpr int OFF = (((DMIN % 4) + 4) % 4);  // staged window starts at a multiple of 4 <= n_tile + DMIN
   constexpr int SPAN = TILE_N + WIN - Q + 4;
   constexpr int SPAN4 = (SPAN + 3) / 4;
-  constexpr int ROW = (SPAN4 * 4 / Q + 2) * SP;
-  __shared__ float zs[N * ROW];
+  constexpr int ROW = Pad<Q>::floats(SPAN4 * 4);
+  __shared__ __align__(16) float zs[N * ROW];
 
   const int b = blockIdx.x / tiles_per_row;
   const int tile = blockIdx.x - b * tiles_per_row;
   const int n_tile = tile * TILE_N;
-  const int first = n_tile + DMIN;
-  const int off = ((first % 4) + 4) % 4;
-  const int g0 = first - off;
+  const int g0 = n_tile + DMIN - OFF;  // multiple of 4
   const bool vec_ok = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
-  const float gain = (float)N;
-  for (int k = 0; k < N; ++k) {
-    const float* zr = z + ((size_t)b * N + k) * L;
-    for (int i4 = threadIdx.x; i4 < SPAN4; i4 += PQ_THREADS) {
-      const int g = g0 + 4 * i4;
-      float4 v;
-      if (vec_ok && g >= 0 && g + 3 < L) {
-        v = __ldg(reinterpret_cast<const float4*>(zr + g));
-      } else {
-        v.x = (g + 0 >= 0 && g + 0 < L) ? __ldg(zr + g + 0) : 0.0f;
-        v.y = (g + 1 >= 0 && g + 1 < L) ? __ldg(zr + g + 1) : 0.0f;
-        v.z = (g + 2 >= 0 && g + 2 < L) ? __ldg(zr + g + 2) : 0.0f;
-        v.w = (g + 3 >= 0 && g + 3 < L) ? __ldg(zr + g + 3) : 0.0f;
-      }
-      const float e[4] = {v.x * gain, v.y * gain, v.z * gain, v.w * gain};  // fp32 N*z like conv_transpose1d
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int i = 4 * i4 + c;
-        zs[k * ROW + (i / Q) * SP + (i % Q)] = e[c];
-      }
-    }
-  }
+  // fp32 product N*z like conv_transpose1d with the updown filter scaled by N (pqmf.py:53)
+  for (int k = 0; k < N; ++k) stage_row<Q, SPAN4>(zs + k * ROW, z + ((size_t)b * N + k) * L, g0, L, (float)N, vec_ok);
   __syncthreads();
 
   float acc[Q][N];
@@ -239,12 +259,7 @@ k_pqmf_synthesis(const float* __restrict__ z, float* __restrict__ y, int L, int 
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     float w[WIN];
-    const int base = threadIdx.x * Q + off;  // tile-local index of z[n0 + DMIN]
-#pragma unroll
-    for (int c = 0; c < WIN; ++c) {
-      const int i = base + c;
-      w[c] = zs[k * ROW + (i / Q) * SP + (i % Q)];
-    }
+    load_window<Q, OFF, WIN>(zs + k * ROW, w);
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const float g = taps.h[k * K + j];
