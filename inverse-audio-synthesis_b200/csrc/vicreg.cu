@@ -27,8 +27,8 @@ constexpr int COLSUM_ROWS = 128;  // rows per k_colsum CTA
 constexpr int MAX_SPLITS = 64;
 
 struct Plan {
-  int B, D, DT, Dp, KB, ntiles, splits, P;
-  size_t off_partial, off_varpart, off_repr, off_mean, off_packed, off_gram, off_covp, off_diag, off_stats, total;
+  int B, D, DT, Dp, KB, ntiles, splits, P, MT;
+  size_t off_partial, off_varpart, off_repr, off_mean, off_packed, off_gram, off_covp, off_diag, off_stats, off_gfull, off_rowpack, off_gpack, total;
 };
 
 __host__ inline Plan make_plan(int B, int D) {
@@ -61,6 +61,10 @@ __host__ inline Plan make_plan(int B, int D) {
   p.off_covp = take((size_t)2 * p.ntiles * TILE);
   p.off_diag = take((size_t)2 * p.Dp);
   p.off_stats = take((size_t)8 * p.Dp);
+  p.MT = (B + TILE - 1) / TILE;
+  p.off_gfull = take((size_t)2 * p.Dp * p.Dp);
+  p.off_rowpack = take((size_t)2 * 2 * p.MT * (p.Dp / KBLK) * TILE_FLOATS);
+  p.off_gpack = take((size_t)2 * 2 * p.DT * (p.Dp / KBLK) * TILE_FLOATS);
   p.total = o;
   return p;
 }
@@ -226,29 +230,18 @@ struct GramSmem {
   uint32_t tmem_base;
 };
 
-// grid = 2 * ntiles * splits, block = 128 (warp 0 lane 0: bulk-copy producer, warp 1 lane 0: MMA issuer, all: epilogue)
-__global__ void __launch_bounds__(128, 1) k_gram_tc(const float* __restrict__ packed, float* __restrict__ gram_partial,
-                                                    int DT, int KB, int ntiles, int splits) {
-  extern __shared__ uint8_t smem_raw[];
-  GramSmem& sm = *reinterpret_cast<GramSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One CTA-wide tcgen05 pass: D[128 x 128] (TMEM, fp32) = sum over nkb K-blocks of A_kb (128 x 32) * B_kb (128 x 32)^T
+// with every operand split into tf32 hi + lo tile images (3 MMAs per k-step: hi*hi + hi*lo + lo*hi).
+// Warp 0 lane 0 feeds a STAGES-deep ring of 16 KiB cp.async.bulk copies, warp 1 lane 0 issues the MMAs, warp 2 owns
+// the TMEM allocation.  Returns the TMEM base address once the accumulator is complete and visible to all threads.
+struct TileStream {
+  const float* hi;    // first K-block of the hi tile images
+  const float* lo;    // first K-block of the lo tile images
+  size_t kb_stride;   // floats between consecutive K-blocks
+};
 
-  int u = blockIdx.x;
-  const int split = u % splits;
-  u /= splits;
-  const int t = u % ntiles;
-  const int s = u / ntiles;
-  int tm = 0, rem = t;  // upper-triangular tile index -> (tm, tn), tn >= tm
-  while (rem >= DT - tm) {
-    rem -= DT - tm;
-    ++tm;
-  }
-  const int tn = tm + rem;
-  const bool diag = (tm == tn);
-  const int kb0 = (int)((long long)KB * split / splits);
-  const int kb1 = (int)((long long)KB * (split + 1) / splits);
-  const int nkb = kb1 - kb0;
-
+__device__ __forceinline__ uint32_t tc_setup(GramSmem& sm) {
+  const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&sm.full[i], 1);
@@ -266,24 +259,23 @@ __global__ void __launch_bounds__(128, 1) k_gram_tc(const float* __restrict__ pa
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = sm.tmem_base;
+  return sm.tmem_base;
+}
 
-  const size_t part_stride = (size_t)DT * KB * TILE_FLOATS;  // hi -> lo
-  const float* a_hi = packed + (((size_t)s * 2 + 0) * DT + tm) * KB * TILE_FLOATS;
-  const float* b_hi = packed + (((size_t)s * 2 + 0) * DT + tn) * KB * TILE_FLOATS;
-
+__device__ __forceinline__ void tc_mainloop(GramSmem& sm, uint32_t tmem, TileStream A, TileStream Bm, bool same,
+                                            int nkb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     // ---- producer: one elected thread feeds the ring with 16 KiB bulk copies ----
     for (int i = 0; i < nkb; ++i) {
       const int st = i % STAGES;
       if (i >= STAGES) mbar_wait(&sm.empty[st], ((i / STAGES) - 1) & 1);
-      const size_t koff = (size_t)(kb0 + i) * TILE_FLOATS;
-      mbar_expect_tx(&sm.full[st], diag ? 2 * TILE_BYTES : 4 * TILE_BYTES);
-      bulk_g2s(sm.tile[st][0], a_hi + koff, TILE_BYTES, &sm.full[st]);
-      bulk_g2s(sm.tile[st][1], a_hi + part_stride + koff, TILE_BYTES, &sm.full[st]);
-      if (!diag) {
-        bulk_g2s(sm.tile[st][2], b_hi + koff, TILE_BYTES, &sm.full[st]);
-        bulk_g2s(sm.tile[st][3], b_hi + part_stride + koff, TILE_BYTES, &sm.full[st]);
+      mbar_expect_tx(&sm.full[st], same ? 2 * TILE_BYTES : 4 * TILE_BYTES);
+      bulk_g2s(sm.tile[st][0], A.hi + (size_t)i * A.kb_stride, TILE_BYTES, &sm.full[st]);
+      bulk_g2s(sm.tile[st][1], A.lo + (size_t)i * A.kb_stride, TILE_BYTES, &sm.full[st]);
+      if (!same) {
+        bulk_g2s(sm.tile[st][2], Bm.hi + (size_t)i * Bm.kb_stride, TILE_BYTES, &sm.full[st]);
+        bulk_g2s(sm.tile[st][3], Bm.lo + (size_t)i * Bm.kb_stride, TILE_BYTES, &sm.full[st]);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -293,8 +285,8 @@ __global__ void __launch_bounds__(128, 1) k_gram_tc(const float* __restrict__ pa
       mbar_wait(&sm.full[st], (i / STAGES) & 1);
       tc_fence_after();
       const uint32_t ah = smem_u32(sm.tile[st][0]), al = smem_u32(sm.tile[st][1]);
-      const uint32_t bh = diag ? ah : smem_u32(sm.tile[st][2]);
-      const uint32_t bl = diag ? al : smem_u32(sm.tile[st][3]);
+      const uint32_t bh = same ? ah : smem_u32(sm.tile[st][2]);
+      const uint32_t bl = same ? al : smem_u32(sm.tile[st][3]);
 #pragma unroll
       for (int k = 0; k < KBLK / 8; ++k) {  // UMMA_K = 8 for tf32 = 32 bytes along the swizzle row
         const uint64_t dah = umma_desc_sw128(ah + 32 * k), dal = umma_desc_sw128(al + 32 * k);
@@ -308,41 +300,208 @@ __global__ void __launch_bounds__(128, 1) k_gram_tc(const float* __restrict__ pa
     tc_commit(&sm.done);  // accumulator complete
   }
   __syncwarp();
-
-  // ---- epilogue: TMEM -> registers -> partial tile (row = TMEM lane = thread) ----
   mbar_wait(&sm.done, 0);
   tc_fence_after();
+}
+
+// 32 fp32 accumulators of this thread's TMEM lane (= output row), columns [c0, c0 + 32)
+__device__ __forceinline__ void tc_load32(uint32_t tmem, int c0, uint32_t (&r)[32]) {
+  const uint32_t taddr = tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + (uint32_t)c0;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_teardown(uint32_t tmem) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TILE) : "memory");
+  }
+}
+
+__device__ __forceinline__ GramSmem& aligned_smem(uint8_t* raw) {
+  return *reinterpret_cast<GramSmem*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+}
+
+// Forward Gram.  grid = 2 * ntiles * splits, block = 128.
+__global__ void __launch_bounds__(128, 1) k_gram_tc(const float* __restrict__ packed, float* __restrict__ gram_partial,
+                                                    int DT, int KB, int ntiles, int splits) {
+  extern __shared__ uint8_t smem_raw[];
+  GramSmem& sm = aligned_smem(smem_raw);
+  int u = blockIdx.x;
+  const int split = u % splits;
+  u /= splits;
+  const int t = u % ntiles;
+  const int s = u / ntiles;
+  int tm = 0, rem = t;  // upper-triangular tile index -> (tm, tn), tn >= tm
+  while (rem >= DT - tm) {
+    rem -= DT - tm;
+    ++tm;
+  }
+  const int tn = tm + rem;
+  const int kb0 = (int)((long long)KB * split / splits);
+  const int kb1 = (int)((long long)KB * (split + 1) / splits);
+  const int nkb = kb1 - kb0;
+  const uint32_t tmem = tc_setup(sm);
+
+  const size_t part_stride = (size_t)DT * KB * TILE_FLOATS;  // hi -> lo
+  TileStream A, Bm;
+  A.hi = packed + ((((size_t)s * 2 + 0) * DT + tm) * KB + kb0) * TILE_FLOATS;
+  A.lo = A.hi + part_stride;
+  A.kb_stride = TILE_FLOATS;
+  Bm.hi = packed + ((((size_t)s * 2 + 0) * DT + tn) * KB + kb0) * TILE_FLOATS;
+  Bm.lo = Bm.hi + part_stride;
+  Bm.kb_stride = TILE_FLOATS;
+  tc_mainloop(sm, tmem, A, Bm, tm == tn, nkb);
+
+  // ---- epilogue: TMEM -> registers -> partial tile (row = TMEM lane = thread) ----
   float* dst = gram_partial + ((((size_t)s * ntiles + t) * splits + split) * TILE + threadIdx.x) * TILE;
 #pragma unroll
   for (int c0 = 0; c0 < TILE; c0 += 32) {
     uint32_t r[32];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (nkb > 0) {
+    tc_load32(tmem, c0, r);
 #pragma unroll
-      for (int c = 0; c < 32; c += 4)
-        *reinterpret_cast<float4*>(dst + c0 + c) = make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]),
-                                                               __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
-    } else {
+    for (int c = 0; c < 32; c += 4)
+      *reinterpret_cast<float4*>(dst + c0 + c) =
+          nkb > 0 ? make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]),
+                                __uint_as_float(r[c + 3]))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  tc_teardown(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward: d loss / d x, d y.
+//   gx[r][d] = kappa * sum_j xc[r][j] * offG_x[j][d]  +  xc[r][d] * s_x[d]  +  c_r * (x[r][d] - y[r][d])
+//   gy likewise with -c_r;  offG = Gram with zero diagonal, s[d] = c_std * (std < 1 ? -1 / (2 D std (B-1)) : 0),
+//   kappa = c_cov * 4 / (embeddim (n-1)^2),  c_r = c_repr * 2 / (B_local D) on the local rows, 0 elsewhere.
+// The contraction is the same tcgen05 pass with A = 128 batch rows of X_c (K-major as stored) and B = 128 rows of offG.
+// ------------------------------------------------------------------------------------------------------------
+// k_pack_rows: grid = (MT, 2), block = 256: centred rows -> tile images [side][part][mt][kbd]
+__global__ void __launch_bounds__(256) k_pack_rows(const float* __restrict__ x, const float* __restrict__ y, int B, int D,
+                                                   int Dp, const float* __restrict__ mean, float* __restrict__ rowpack,
+                                                   int MT) {
+  const int mt = blockIdx.x, s = blockIdx.y;
+  const float* src = s ? y : x;
+  const int KBD = Dp / KBLK;
+  const int f4_per_row = Dp / 4;
+  for (int f = threadIdx.x; f < TILE * f4_per_row; f += blockDim.x) {
+    const int rl = f / f4_per_row, c4 = f - rl * f4_per_row;
+    const int d = 4 * c4, row = mt * TILE + rl;
+    float v[4];
 #pragma unroll
-      for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dst + c0 + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < 4; ++e)
+      v[e] = (row < B && d + e < D) ? __ldg(src + (size_t)row * D + d + e) - mean[s * D + d + e] : 0.0f;
+    float4 h, l;
+    h.x = to_tf32(v[0]); h.y = to_tf32(v[1]); h.z = to_tf32(v[2]); h.w = to_tf32(v[3]);
+    l.x = to_tf32(v[0] - h.x); l.y = to_tf32(v[1] - h.y); l.z = to_tf32(v[2] - h.z); l.w = to_tf32(v[3] - h.w);
+    const int kb = d / KBLK, c = (d % KBLK) / 4;
+    const size_t off = (size_t)(rl >> 3) * 256 + (rl & 7) * 32 + ((c ^ (rl & 7)) * 4);
+    float* hi = rowpack + ((((size_t)s * 2 + 0) * MT + mt) * KBD + kb) * TILE_FLOATS;
+    float* lo = rowpack + ((((size_t)s * 2 + 1) * MT + mt) * KBD + kb) * TILE_FLOATS;
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+// k_pack_offg: grid = (DT, 2), block = 256: Gram with zero diagonal -> tile images [side][part][nt][kbd]
+__global__ void __launch_bounds__(256) k_pack_offg(const float* __restrict__ gram_full, int Dp,
+                                                   float* __restrict__ gpack, int DT) {
+  const int nt = blockIdx.x, s = blockIdx.y;
+  const int KBD = Dp / KBLK;
+  const int f4_per_row = Dp / 4;
+  for (int f = threadIdx.x; f < TILE * f4_per_row; f += blockDim.x) {
+    const int rl = f / f4_per_row, c4 = f - rl * f4_per_row;
+    const int d = 4 * c4, row = nt * TILE + rl;
+    float4 g = *reinterpret_cast<const float4*>(gram_full + ((size_t)s * Dp + row) * Dp + d);
+    float v[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (d + e == row) v[e] = 0.0f;
+    float4 h, l;
+    h.x = to_tf32(v[0]); h.y = to_tf32(v[1]); h.z = to_tf32(v[2]); h.w = to_tf32(v[3]);
+    l.x = to_tf32(v[0] - h.x); l.y = to_tf32(v[1] - h.y); l.z = to_tf32(v[2] - h.z); l.w = to_tf32(v[3] - h.w);
+    const int kb = d / KBLK, c = (d % KBLK) / 4;
+    const size_t off = (size_t)(rl >> 3) * 256 + (rl & 7) * 32 + ((c ^ (rl & 7)) * 4);
+    float* hi = gpack + ((((size_t)s * 2 + 0) * DT + nt) * KBD + kb) * TILE_FLOATS;
+    float* lo = gpack + ((((size_t)s * 2 + 1) * DT + nt) * KBD + kb) * TILE_FLOATS;
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+struct BwdArgs {
+  const float* x;
+  const float* y;
+  const float* mean;     // [2][D]
+  const float* stdv;     // [2][Dp]
+  const float* gout4;    // device: upstream grads of {loss, repr, std, cov}
+  const float* rowpack;
+  const float* gpack;
+  float* gx;
+  float* gy;
+  int B, D, Dp, DT, MT, local_row0, B_local, cfgB, embeddim;
+  float sim, stdc, covc;
+};
+
+// grid = 2 * MT * DT, block = 128
+__global__ void __launch_bounds__(128, 1) k_bwd_tc(BwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  GramSmem& sm = aligned_smem(smem_raw);
+  int u = blockIdx.x;
+  const int nt = u % a.DT;
+  u /= a.DT;
+  const int mt = u % a.MT;
+  const int s = u / a.MT;
+  const int KBD = a.Dp / KBLK;
+  const uint32_t tmem = tc_setup(sm);
+  TileStream A, Bm;
+  A.hi = a.rowpack + ((((size_t)s * 2 + 0) * a.MT + mt) * KBD) * TILE_FLOATS;
+  A.lo = a.rowpack + ((((size_t)s * 2 + 1) * a.MT + mt) * KBD) * TILE_FLOATS;
+  A.kb_stride = TILE_FLOATS;
+  Bm.hi = a.gpack + ((((size_t)s * 2 + 0) * a.DT + nt) * KBD) * TILE_FLOATS;
+  Bm.lo = a.gpack + ((((size_t)s * 2 + 1) * a.DT + nt) * KBD) * TILE_FLOATS;
+  Bm.kb_stride = TILE_FLOATS;
+  tc_mainloop(sm, tmem, A, Bm, false, KBD);
+
+  const float g0 = a.gout4[0], g1 = a.gout4[1], g2 = a.gout4[2], g3 = a.gout4[3];
+  const float c_std = g0 * a.stdc + g2;
+  const float n1 = (float)(a.cfgB - 1);
+  const float kappa = (g0 * a.covc + g3) * 4.0f / ((float)a.embeddim * n1 * n1);
+  const int row = mt * TILE + threadIdx.x;
+  const bool local = row >= a.local_row0 && row < a.local_row0 + a.B_local;
+  float c_r = local ? (g0 * a.sim + g1) * 2.0f / ((float)a.B_local * (float)a.D) : 0.0f;
+  if (s) c_r = -c_r;
+  const float s_scale = -c_std / (2.0f * (float)a.D * (float)(a.B - 1));
+  float* dst = s ? a.gy : a.gx;
+#pragma unroll
+  for (int c0 = 0; c0 < TILE; c0 += 32) {
+    uint32_t r[32];
+    tc_load32(tmem, c0, r);
+    if (row < a.B) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int d = nt * TILE + c0 + c;
+        if (d < a.D) {
+          const float xv = __ldg(a.x + (size_t)row * a.D + d), yv = __ldg(a.y + (size_t)row * a.D + d);
+          const float ov = s ? yv : xv;
+          const float sd = a.stdv[s * a.Dp + d];
+          const float sg = sd < 1.0f ? s_scale / sd : 0.0f;
+          dst[(size_t)row * a.D + d] = kappa * __uint_as_float(r[c]) + (ov - a.mean[s * a.D + d]) * sg + c_r * (xv - yv);
+        }
+      }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TILE) : "memory");
-  }
+  tc_teardown(tmem);
 }
 
 // Plain CUDA-core Gram of the same packed operands' source (test hook): gram[D][D] = xc^T xc in fp32.
@@ -548,7 +707,7 @@ extern "C" int ias_vicreg_loss(const float* x, const float* y, int B, int local_
   const Plan p = make_plan(B, D);
   float* w = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
-  rc = run_stats_and_gram(x, y, p, local_row0, B_local, w, nullptr, st);
+  rc = run_stats_and_gram(x, y, p, local_row0, B_local, w, w + p.off_gfull, st);
   if (rc) return rc;
   FinalArgs a;
   a.repr = w + p.off_repr;
@@ -606,8 +765,47 @@ extern "C" int ias_vicreg_loss_backward(const float* x, const float* y, int B, i
                                         int cfg_batch_size, int D, int embeddim, float sim_coeff, float std_coeff,
                                         float cov_coeff, const float* gout4, float* gx, float* gy, void* workspace,
                                         size_t workspace_bytes, ias_stream_t stream) {
-  (void)x; (void)y; (void)B; (void)local_row0; (void)B_local; (void)cfg_batch_size; (void)D; (void)embeddim;
-  (void)sim_coeff; (void)std_coeff; (void)cov_coeff; (void)gout4; (void)gx; (void)gy; (void)workspace;
-  (void)workspace_bytes; (void)stream;
-  return ias::set_err(IAS_ERR_UNSUPPORTED, "ias_vicreg_loss_backward: not implemented yet (SURVEY 8f row 1)");
+  int rc = check_common(x, B, D, workspace, workspace_bytes, "ias_vicreg_loss_backward");
+  if (rc) return rc;
+  IAS_REQUIRE(y && gout4 && gx && gy, IAS_ERR_INVALID, "ias_vicreg_loss_backward: NULL pointer");
+  IAS_REQUIRE(local_row0 >= 0 && B_local > 0 && local_row0 + B_local <= B, IAS_ERR_INVALID,
+              "ias_vicreg_loss_backward: local rows [%d,%d) outside [0,%d)", local_row0, local_row0 + B_local, B);
+  IAS_REQUIRE(B > 1 && cfg_batch_size != 1 && embeddim > 0, IAS_ERR_INVALID,
+              "ias_vicreg_loss_backward: B=%d cfg_batch_size=%d embeddim=%d", B, cfg_batch_size, embeddim);
+  const Plan p = make_plan(B, D);
+  float* w = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  {
+    ProfScope prof_(K_VICREG_BWD, st);
+    k_pack_rows<<<dim3(p.MT, 2), 256, 0, st>>>(x, y, B, D, p.Dp, w + p.off_mean, w + p.off_rowpack, p.MT);
+  }
+  IAS_LAUNCH_CHECK("k_pack_rows");
+  {
+    ProfScope prof_(K_VICREG_BWD, st);
+    k_pack_offg<<<dim3(p.DT, 2), 256, 0, st>>>(w + p.off_gfull, p.Dp, w + p.off_gpack, p.DT);
+  }
+  IAS_LAUNCH_CHECK("k_pack_offg");
+  static bool attr_set = false;
+  const int smem = (int)sizeof(GramSmem) + 1024;
+  if (!attr_set) {
+    IAS_CUDA(cudaFuncSetAttribute(k_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  BwdArgs a;
+  a.x = x; a.y = y;
+  a.mean = w + p.off_mean;
+  a.stdv = w + p.off_stats;
+  a.gout4 = gout4;
+  a.rowpack = w + p.off_rowpack;
+  a.gpack = w + p.off_gpack;
+  a.gx = gx; a.gy = gy;
+  a.B = B; a.D = D; a.Dp = p.Dp; a.DT = p.DT; a.MT = p.MT;
+  a.local_row0 = local_row0; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
+  a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
+  {
+    ProfScope prof_(K_VICREG_BWD, st);
+    k_bwd_tc<<<2 * p.MT * p.DT, 128, smem, st>>>(a);
+  }
+  IAS_LAUNCH_CHECK("k_bwd_tc");
+  return IAS_OK;
 }

@@ -98,6 +98,63 @@ def test_loss_is_deterministic_and_handles_local_rows(cuda_device):
     assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]
 
 
+@pytest.mark.parametrize("name,B,D,kind,cfgB,E", MG.VICREG_CASES)
+def test_backward_vs_reference_goldens(cuda_device, name, B, D, kind, cfgB, E):
+    """d loss / d x, d y through the autograd Function (tcgen05 backward GEMM) vs torch autograd on the reference."""
+    import ias_b200
+
+    gold = np.load(os.path.join(GOLDEN, "vicreg_cases.npz"))
+    x, y = MG.vicreg_inputs(B, D, kind)
+    xd = x.to(cuda_device).requires_grad_(True)
+    yd = y.to(cuda_device).requires_grad_(True)
+    m = ias_b200.VICReg(_cfg(D, E, cfgB), torch.nn.Identity(), torch.nn.Identity())
+    out = m.loss(xd, yd)
+    out[0].backward()
+    gx, gy = xd.grad.cpu().numpy(), yd.grad.cpu().numpy()
+    if B <= 128:
+        rx, ry = gold[f"{name}_gx"], gold[f"{name}_gy"]
+    else:
+        gx, gy, rx, ry = gx[::64], gy[::64], gold[f"{name}_gx_sub"], gold[f"{name}_gy_sub"]
+    ex = np.abs(gx - rx).max() / np.abs(rx).max()
+    ey = np.abs(gy - ry).max() / np.abs(ry).max()
+    print(f"{name}: grad rel err x {ex:.2e} y {ey:.2e}")
+    assert ex <= 1e-4 and ey <= 1e-4
+
+
+def test_backward_of_individual_terms_and_local_rows(cuda_device):
+    from ias_b200.vicreg import vicreg_loss
+
+    B, D = 512, 256
+    x, y = MG.vicreg_inputs(B, D, "correlated", seed=8)
+    xd = x.to(cuda_device).requires_grad_(True)
+    yd = y.to(cuda_device).requires_grad_(True)
+    out = vicreg_loss(xd, yd, B, D, 25.0, 25.0, 1.0)
+    (2.0 * out[1] + 3.0 * out[3] + 0.5 * out[2]).backward()
+    gx, gy = OV.loss_grad(x.numpy(), y.numpy(), B, D, sim_coeff=2.0, std_coeff=0.5, cov_coeff=3.0)
+    assert np.abs(xd.grad.cpu().numpy() - gx).max() <= 1e-4 * np.abs(gx).max()
+    assert np.abs(yd.grad.cpu().numpy() - gy).max() <= 1e-4 * np.abs(gy).max()
+    # local rows: the invariance gradient lives only on [row0, row0 + b_local) and is scaled by 1 / b_local
+    from ias_b200 import _lib
+    import ias_b200
+
+    lib = ias_b200.lib()
+    ws = _ws(B, D, cuda_device)
+    out4 = torch.empty(4, device=cuda_device)
+    xc, yc = x.to(cuda_device), y.to(cuda_device)
+    st = _lib.current_stream(cuda_device)
+    _lib.check(lib.ias_vicreg_loss(_lib.ptr(xc), _lib.ptr(yc), B, 128, 64, B, D, D, 25.0, 25.0, 1.0, _lib.ptr(out4),
+                                   _lib.ptr(ws), ws.numel() * 4, st))
+    gout = torch.tensor([0.0, 1.0, 0.0, 0.0], device=cuda_device)
+    gxd, gyd = torch.empty_like(xc), torch.empty_like(yc)
+    _lib.check(lib.ias_vicreg_loss_backward(_lib.ptr(xc), _lib.ptr(yc), B, 128, 64, B, D, D, 25.0, 25.0, 1.0,
+                                            _lib.ptr(gout), _lib.ptr(gxd), _lib.ptr(gyd), _lib.ptr(ws), ws.numel() * 4,
+                                            st))
+    want = torch.zeros_like(x)
+    want[128:192] = 2.0 * (x[128:192] - y[128:192]) / (64 * D)
+    assert float((gxd.cpu() - want).abs().max()) <= 1e-6 * float(want.abs().max())
+    assert float((gyd.cpu() + want).abs().max()) <= 1e-6 * float(want.abs().max())
+
+
 def test_bad_arguments_fail_loudly(cuda_device):
     from ias_b200 import _lib
     import ias_b200
