@@ -145,7 +145,7 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
   __syncthreads();
   if (tid < 6) {
     const int base[6] = {ADSR1, ADSR2, LFO1_AMP, LFO2_AMP, LFO1_RATE, LFO2_RATE};
-    sh.adsr[tid] = adsr_setup(&sh.P[base[tid]], sh.P[KEY_DURATION], cr);
+    sh.adsr[tid] = adsr_setup(&sh.P[base[tid]], sh.P[KEY_DURATION], cr, eps);
   } else if (tid < 8) {
     sh.lfo[tid - 6] = lfo_setup(&sh.P[tid == 6 ? LFO1 : LFO2]);
   } else if (tid == 8) {

@@ -292,10 +292,26 @@ inline RangeTable make_range_table() {
 struct Adsr {
   float a_dur, d_dur, d_start, r_dur, r_start;  // control-rate samples
   float sustain, one_minus_sustain, alpha;
+  float d_pre, r_pre;  // value of the decay / release ramp at every n <= its start (max(n - start, 0) == 0 there)
 };
 
+IAS_HD float adsr_ramp(float n, float dur, float start, bool inverse, float alpha, float eps) {
+  float r = fmaxf(sub(n, start), 0.0f);
+  r = add(div(add(r, eps), dur), eps);
+  r = fminf(r, 1.0f);
+  if (inverse && dur > 0.0f) r = sub(1.0f, r);
+  return pow_sleef(r, alpha);
+}
+
+// Call after the other fields are set: the inverse ramps are constant up to their start sample, so that value
+// (the same expression evaluated once) replaces a pow per control point there.
+IAS_HD void adsr_precompute(Adsr& p, float eps) {
+  p.d_pre = adsr_ramp(0.0f, p.d_dur, 0.0f, true, p.alpha, eps);
+  p.r_pre = adsr_ramp(0.0f, p.r_dur, 0.0f, true, p.alpha, eps);
+}
+
 // v[] = {attack, decay, sustain, release, alpha} already through from_0to1.
-IAS_HD Adsr adsr_setup(const float* v, float note_on, float cr) {
+IAS_HD Adsr adsr_setup(const float* v, float note_on, float cr, float eps) {
   Adsr p;
   float new_attack = fminf(v[0], note_on);
   float new_decay = fminf(fmaxf(sub(note_on, v[0]), 0.0f), v[1]);
@@ -307,22 +323,15 @@ IAS_HD Adsr adsr_setup(const float* v, float note_on, float cr) {
   p.sustain = v[2];
   p.one_minus_sustain = sub(1.0f, v[2]);
   p.alpha = v[4];
+  adsr_precompute(p, eps);
   return p;
-}
-
-IAS_HD float adsr_ramp(float n, float dur, float start, bool inverse, float alpha, float eps) {
-  float r = fmaxf(sub(n, start), 0.0f);
-  r = add(div(add(r, eps), dur), eps);
-  r = fminf(r, 1.0f);
-  if (inverse && dur > 0.0f) r = sub(1.0f, r);
-  return pow_sleef(r, alpha);
 }
 
 IAS_HD float adsr_eval(const Adsr& p, float n, float eps) {
   float a = adsr_ramp(n, p.a_dur, 0.0f, false, p.alpha, eps);
-  float d = adsr_ramp(n, p.d_dur, p.d_start, true, p.alpha, eps);
+  float d = n <= p.d_start ? p.d_pre : adsr_ramp(n, p.d_dur, p.d_start, true, p.alpha, eps);
   float dk = add(mul(p.one_minus_sustain, d), p.sustain);
-  float r = adsr_ramp(n, p.r_dur, p.r_start, true, p.alpha, eps);
+  float r = n <= p.r_start ? p.r_pre : adsr_ramp(n, p.r_dur, p.r_start, true, p.alpha, eps);
   return mul(mul(a, dk), r);
 }
 

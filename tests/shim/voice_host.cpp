@@ -34,7 +34,7 @@ void shim_control(const float* params01, int B, int C, float cr, float eps, floa
     for (int r = 0; r < NROWS; ++r) P[r] = from_0to1(params01[(size_t)r * B + b], t.r[r]);
     const int base[6] = {ADSR1, ADSR2, LFO1_AMP, LFO2_AMP, LFO1_RATE, LFO2_RATE};
     Adsr ad[6];
-    for (int i = 0; i < 6; ++i) ad[i] = adsr_setup(&P[base[i]], P[KEY_DURATION], cr);
+    for (int i = 0; i < 6; ++i) ad[i] = adsr_setup(&P[base[i]], P[KEY_DURATION], cr, eps);
     Lfo lf[2] = {lfo_setup(&P[LFO1]), lfo_setup(&P[LFO2])};
     ModMatrix mm = modmatrix_setup(&P[MODM]);
     voice_constants(P, vconst + (size_t)b * VC_COUNT);
