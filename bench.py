@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--bands", type=int, default=3)
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused = loss kernels read peers' embeddings over NVLink (symmetric memory); "
+                         "nccl = FullGatherLayer all-gather through torch.distributed")
     ap.add_argument("--cpu-sample", type=int, default=128, help="sounds per CPU-baseline step (config 1: 128)")
     return ap.parse_args()
 
@@ -187,6 +190,8 @@ def run_ours(args):
         mlp="8-8-%d", batch_size=B * world, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
     vic = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity())
     wa, wp = harness.bridge_weights(dev)
+    if world > 1 and args.gather == "fused":
+        ias_b200.use_fused_gather(ias_b200.EmbeddingExchange(B, D, dev))
 
     def step(i: int):
         audio, params, _ = voice(i * world + rank)       # sound ids [ (i*W + r) * B, ... ): SURVEY 8(d) config 4
@@ -324,7 +329,8 @@ def run_ours(args):
         "config": {
             "workload": ("BASELINE configs[3] shard: front end synth->PQMF(N=%d)->VICReg(D=256), %d sounds x %g s @ 44.1 kHz "
                          "per GPU, global batch %d, embedding all-gather %s" % (
-                             args.bands, B, args.seconds, B * world, "over NCCL" if world > 1 else "n/a at N=1")),
+                             args.bands, B, args.seconds, B * world, ("fused into the loss kernels over NVLink peer memory" if args.gather == "fused" else "over NCCL")
+                             if world > 1 else "n/a at N=1")),
             "per_gpu_batch": B, "global_batch": B * world, "seconds": args.seconds, "bands": args.bands,
             "noise": "reproducible (32-row table)",
             "l2": "inputs larger than L2: 722 MB audio + 722 MB bands per step vs 126 MB L2",

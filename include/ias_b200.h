@@ -135,6 +135,24 @@ IAS_API int ias_vicreg_loss_backward(const float* x, const float* y, int B, int 
                              const float* gout4, float* gx, float* gy, void* workspace, size_t workspace_bytes,
                              ias_stream_t stream);
 
+/* Fused embedding all-gather + loss (replaces FullGatherLayer + loss, vicreg.py:36-58 with 38-39 live).
+ * x_peers_host[q] / y_peers_host[q] (host arrays of `world` DEVICE pointers, rank order) address rank q's
+ * [B_local][D] embeddings in peer-accessible memory (e.g. torch symmetric memory): the column-statistics kernel reads
+ * them over NVLink itself and keeps a local copy of the gathered batch in the workspace -- there is no separate
+ * all-gather launch.  The caller must have made every rank's buffer visible (a barrier on the stream) before the call
+ * and must not overwrite its own buffer until every rank's call has completed.  Invariance term: rows of `rank`. */
+IAS_API size_t ias_vicreg_gather_workspace_bytes(int world, int B_local, int D);
+IAS_API int ias_vicreg_loss_gather(const float* const* x_peers_host, const float* const* y_peers_host, int world, int rank,
+                           int B_local, int cfg_batch_size, int D, int embeddim, float sim_coeff, float std_coeff,
+                           float cov_coeff, float* out4, void* workspace, size_t workspace_bytes, ias_stream_t stream);
+/* Gradient w.r.t. this rank's own rows, summed over all ranks' losses (what FullGatherLayer.backward delivers): the
+ * std/cov part is identical on every rank, so it is `world` times the own-row slice and needs no communication.
+ * gx_local, gy_local: [B_local][D].  Uses the workspace of the preceding ias_vicreg_loss_gather. */
+IAS_API int ias_vicreg_loss_gather_backward(int world, int rank, int B_local, int cfg_batch_size, int D, int embeddim,
+                                    float sim_coeff, float std_coeff, float cov_coeff, const float* gout4,
+                                    float* gx_local, float* gy_local, void* workspace, size_t workspace_bytes,
+                                    ias_stream_t stream);
+
 /* Test hook: plain CUDA-core Gram of the centred matrix, gram[D][D] = xc^T xc, to cross-check the tcgen05 path. */
 IAS_API int ias_vicreg_gram_reference(const float* x, int B, int D, float* gram, void* workspace, size_t workspace_bytes,
                               ias_stream_t stream);

@@ -72,9 +72,19 @@ __host__ inline Plan make_plan(int B, int D) {
 // ------------------------------------------------------------------------------------------------------------
 // k_colsum: grid = P, block = 256.  partial[p][s][d] = sum over the CTA's rows; repr[p] = sum (x-y)^2 over local rows
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ x, const float* __restrict__ y, int B, int D,
-                                                int local_row0, int local_rows, float* __restrict__ partial,
-                                                float* __restrict__ repr) {
+// Where the rows of the (global) batch live: rank q owns rows [q*rows_per, (q+1)*rows_per).  Single process: one
+// entry.  Multi-GPU fused gather: the entries are peer pointers into every rank's symmetric-memory buffer, read over
+// NVLink by the statistics kernel itself (no separate all-gather launch, no NCCL on the data path).
+constexpr int MAX_PEERS = 16;
+struct RowSrc {
+  const float* x[MAX_PEERS];
+  const float* y[MAX_PEERS];
+  int rows_per;
+};
+
+__global__ void __launch_bounds__(256) k_colsum(RowSrc src, int B, int D, int local_row0, int local_rows,
+                                                float* __restrict__ partial, float* __restrict__ repr,
+                                                float* __restrict__ xg, float* __restrict__ yg) {
   __shared__ float s_red[8];
   const int r0 = blockIdx.x * COLSUM_ROWS;
   const int r1 = min(r0 + COLSUM_ROWS, B);
@@ -82,7 +92,14 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ x, con
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float sx = 0.0f, sy = 0.0f;
     for (int r = r0; r < r1; ++r) {
-      const float a = __ldg(x + (size_t)r * D + d), c = __ldg(y + (size_t)r * D + d);
+      const int q = r / src.rows_per;
+      const size_t lo = (size_t)(r - q * src.rows_per) * D + d;
+      // plain (coherent) loads: the peers' buffers were written by other GPUs just before the barrier
+      const float a = src.x[q][lo], c = src.y[q][lo];
+      if (xg) {  // fused all-gather: keep a local copy of the gathered batch for the passes that follow
+        xg[(size_t)r * D + d] = a;
+        yg[(size_t)r * D + d] = c;
+      }
       sx += a;
       sy += c;
       if (r >= local_row0 && r < local_row0 + local_rows) {
@@ -389,14 +406,14 @@ __global__ void __launch_bounds__(128, 1) k_gram_tc(const float* __restrict__ pa
 // k_pack_rows: grid = (MT, 2), block = 256: centred rows -> tile images [side][part][mt][kbd]
 __global__ void __launch_bounds__(256) k_pack_rows(const float* __restrict__ x, const float* __restrict__ y, int B, int D,
                                                    int Dp, const float* __restrict__ mean, float* __restrict__ rowpack,
-                                                   int MT) {
-  const int mt = blockIdx.x, s = blockIdx.y;
+                                                   int MT, int mt0) {
+  const int mt = blockIdx.x, s = blockIdx.y;  // mt counts from the first packed row tile mt0
   const float* src = s ? y : x;
   const int KBD = Dp / KBLK;
   const int f4_per_row = Dp / 4;
   for (int f = threadIdx.x; f < TILE * f4_per_row; f += blockDim.x) {
     const int rl = f / f4_per_row, c4 = f - rl * f4_per_row;
-    const int d = 4 * c4, row = mt * TILE + rl;
+    const int d = 4 * c4, row = (mt0 + mt) * TILE + rl;
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e)
@@ -450,6 +467,10 @@ struct BwdArgs {
   float* gx;
   float* gy;
   int B, D, Dp, DT, MT, local_row0, B_local, cfgB, embeddim;
+  int mt0;        // first row tile computed (MT tiles from there)
+  int out_row0;   // gx/gy hold rows [out_row0, out_row0 + out_rows) of the batch
+  int out_rows;
+  float gscale;   // multiplies the std/cov gradient (world size in the fused-gather path)
   float sim, stdc, covc;
 };
 
@@ -477,17 +498,18 @@ __global__ void __launch_bounds__(128, 1) k_bwd_tc(BwdArgs a) {
   const float c_std = g0 * a.stdc + g2;
   const float n1 = (float)(a.cfgB - 1);
   const float kappa = (g0 * a.covc + g3) * 4.0f / ((float)a.embeddim * n1 * n1);
-  const int row = mt * TILE + threadIdx.x;
+  const int row = (a.mt0 + mt) * TILE + threadIdx.x;
   const bool local = row >= a.local_row0 && row < a.local_row0 + a.B_local;
   float c_r = local ? (g0 * a.sim + g1) * 2.0f / ((float)a.B_local * (float)a.D) : 0.0f;
   if (s) c_r = -c_r;
-  const float s_scale = -c_std / (2.0f * (float)a.D * (float)(a.B - 1));
+  const float s_scale = -a.gscale * c_std / (2.0f * (float)a.D * (float)(a.B - 1));
+  const float kap = kappa * a.gscale;
   float* dst = s ? a.gy : a.gx;
 #pragma unroll
   for (int c0 = 0; c0 < TILE; c0 += 32) {
     uint32_t r[32];
     tc_load32(tmem, c0, r);
-    if (row < a.B) {
+    if (row < a.B && row >= a.out_row0 && row < a.out_row0 + a.out_rows) {
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         const int d = nt * TILE + c0 + c;
@@ -496,7 +518,8 @@ __global__ void __launch_bounds__(128, 1) k_bwd_tc(BwdArgs a) {
           const float ov = s ? yv : xv;
           const float sd = a.stdv[s * a.Dp + d];
           const float sg = sd < 1.0f ? s_scale / sd : 0.0f;
-          dst[(size_t)row * a.D + d] = kappa * __uint_as_float(r[c]) + (ov - a.mean[s * a.D + d]) * sg + c_r * (xv - yv);
+          dst[(size_t)(row - a.out_row0) * a.D + d] =
+              kap * __uint_as_float(r[c]) + (ov - a.mean[s * a.D + d]) * sg + c_r * (xv - yv);
         }
       }
     }
@@ -660,11 +683,21 @@ int launch_gram(const Plan& p, float* w, cudaStream_t st) {
   return IAS_OK;
 }
 
-int run_stats_and_gram(const float* x, const float* y, const Plan& p, int local_row0, int B_local, float* w,
-                       float* gram_full, cudaStream_t st) {
+RowSrc single_src(const float* x, const float* y, int B) {
+  RowSrc s;
+  for (int i = 0; i < MAX_PEERS; ++i) s.x[i] = s.y[i] = nullptr;
+  s.x[0] = x;
+  s.y[0] = y;
+  s.rows_per = B;
+  return s;
+}
+
+// x, y: where the centring/packing passes read the batch (the gathered copy when `src` is a peer table)
+int run_stats_and_gram(const RowSrc& src, const float* x, const float* y, float* xg, float* yg, const Plan& p,
+                       int local_row0, int B_local, float* w, float* gram_full, cudaStream_t st) {
   {
     ProfScope prof_(K_VICREG_COLSUM, st);
-    k_colsum<<<p.P, 256, 0, st>>>(x, y, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr);
+    k_colsum<<<p.P, 256, 0, st>>>(src, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr, xg, yg);
   }
   IAS_LAUNCH_CHECK("k_colsum");
   {
@@ -707,7 +740,7 @@ extern "C" int ias_vicreg_loss(const float* x, const float* y, int B, int local_
   const Plan p = make_plan(B, D);
   float* w = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
-  rc = run_stats_and_gram(x, y, p, local_row0, B_local, w, w + p.off_gfull, st);
+  rc = run_stats_and_gram(single_src(x, y, B), x, y, nullptr, nullptr, p, local_row0, B_local, w, w + p.off_gfull, st);
   if (rc) return rc;
   FinalArgs a;
   a.repr = w + p.off_repr;
@@ -737,7 +770,7 @@ extern "C" int ias_vicreg_gram_tc(const float* x, int B, int D, float* gram, voi
   float* w = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
   // the hook runs x against itself; `gram` receives both (identical) sides, [2][D][D]
-  return run_stats_and_gram(x, x, p, 0, B, w, gram, st);
+  return run_stats_and_gram(single_src(x, x, B), x, x, nullptr, nullptr, p, 0, B, w, gram, st);
 }
 
 extern "C" int ias_vicreg_gram_reference(const float* x, int B, int D, float* gram, void* workspace,
@@ -748,7 +781,7 @@ extern "C" int ias_vicreg_gram_reference(const float* x, int B, int D, float* gr
   const Plan p = make_plan(B, D);
   float* w = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
-  k_colsum<<<p.P, 256, 0, st>>>(x, x, p.B, p.D, 0, B, w + p.off_partial, w + p.off_repr);
+  k_colsum<<<p.P, 256, 0, st>>>(single_src(x, x, B), p.B, p.D, 0, B, w + p.off_partial, w + p.off_repr, nullptr, nullptr);
   IAS_LAUNCH_CHECK("k_colsum");
   k_center_pack<<<dim3(p.P, 2), 256, 0, st>>>(x, x, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
                                               w + p.off_varpart, w + p.off_packed);
@@ -761,23 +794,17 @@ extern "C" int ias_vicreg_gram_reference(const float* x, int B, int D, float* gr
   return IAS_OK;
 }
 
-extern "C" int ias_vicreg_loss_backward(const float* x, const float* y, int B, int local_row0, int B_local,
-                                        int cfg_batch_size, int D, int embeddim, float sim_coeff, float std_coeff,
-                                        float cov_coeff, const float* gout4, float* gx, float* gy, void* workspace,
-                                        size_t workspace_bytes, ias_stream_t stream) {
-  int rc = check_common(x, B, D, workspace, workspace_bytes, "ias_vicreg_loss_backward");
-  if (rc) return rc;
-  IAS_REQUIRE(y && gout4 && gx && gy, IAS_ERR_INVALID, "ias_vicreg_loss_backward: NULL pointer");
-  IAS_REQUIRE(local_row0 >= 0 && B_local > 0 && local_row0 + B_local <= B, IAS_ERR_INVALID,
-              "ias_vicreg_loss_backward: local rows [%d,%d) outside [0,%d)", local_row0, local_row0 + B_local, B);
-  IAS_REQUIRE(B > 1 && cfg_batch_size != 1 && embeddim > 0, IAS_ERR_INVALID,
-              "ias_vicreg_loss_backward: B=%d cfg_batch_size=%d embeddim=%d", B, cfg_batch_size, embeddim);
-  const Plan p = make_plan(B, D);
-  float* w = reinterpret_cast<float*>(workspace);
-  cudaStream_t st = as_stream(stream);
+namespace ias {
+namespace {
+int run_backward(const float* x, const float* y, const Plan& p, int local_row0, int B_local, int cfgB, int embeddim,
+                 float sim, float stdc, float covc, const float* gout4, float* gx, float* gy, int out_row0, int out_rows,
+                 float gscale, float* w, cudaStream_t st) {
+  const int mt0 = out_row0 / TILE;
+  const int mt1 = (out_row0 + out_rows + TILE - 1) / TILE;
+  const int MTn = mt1 - mt0;
   {
     ProfScope prof_(K_VICREG_BWD, st);
-    k_pack_rows<<<dim3(p.MT, 2), 256, 0, st>>>(x, y, B, D, p.Dp, w + p.off_mean, w + p.off_rowpack, p.MT);
+    k_pack_rows<<<dim3(MTn, 2), 256, 0, st>>>(x, y, p.B, p.D, p.Dp, w + p.off_mean, w + p.off_rowpack, MTn, mt0);
   }
   IAS_LAUNCH_CHECK("k_pack_rows");
   {
@@ -799,13 +826,114 @@ extern "C" int ias_vicreg_loss_backward(const float* x, const float* y, int B, i
   a.rowpack = w + p.off_rowpack;
   a.gpack = w + p.off_gpack;
   a.gx = gx; a.gy = gy;
-  a.B = B; a.D = D; a.Dp = p.Dp; a.DT = p.DT; a.MT = p.MT;
-  a.local_row0 = local_row0; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
-  a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
+  a.B = p.B; a.D = p.D; a.Dp = p.Dp; a.DT = p.DT; a.MT = MTn;
+  a.local_row0 = local_row0; a.B_local = B_local; a.cfgB = cfgB; a.embeddim = embeddim;
+  a.mt0 = mt0; a.out_row0 = out_row0; a.out_rows = out_rows; a.gscale = gscale;
+  a.sim = sim; a.stdc = stdc; a.covc = covc;
   {
     ProfScope prof_(K_VICREG_BWD, st);
-    k_bwd_tc<<<2 * p.MT * p.DT, 128, smem, st>>>(a);
+    k_bwd_tc<<<2 * MTn * p.DT, 128, smem, st>>>(a);
   }
   IAS_LAUNCH_CHECK("k_bwd_tc");
   return IAS_OK;
+}
+
+Plan gather_plan(int world, int B_local, int D, size_t* off_xg, size_t* off_yg, size_t* total) {
+  const Plan p = make_plan(world * B_local, D);
+  const size_t n = ((size_t)world * B_local * D + 255) / 256 * 256;
+  *off_xg = p.total;
+  *off_yg = p.total + n;
+  *total = p.total + 2 * n;
+  return p;
+}
+}  // namespace
+}  // namespace ias
+
+extern "C" int ias_vicreg_loss_backward(const float* x, const float* y, int B, int local_row0, int B_local,
+                                        int cfg_batch_size, int D, int embeddim, float sim_coeff, float std_coeff,
+                                        float cov_coeff, const float* gout4, float* gx, float* gy, void* workspace,
+                                        size_t workspace_bytes, ias_stream_t stream) {
+  int rc = check_common(x, B, D, workspace, workspace_bytes, "ias_vicreg_loss_backward");
+  if (rc) return rc;
+  IAS_REQUIRE(y && gout4 && gx && gy, IAS_ERR_INVALID, "ias_vicreg_loss_backward: NULL pointer");
+  IAS_REQUIRE(local_row0 >= 0 && B_local > 0 && local_row0 + B_local <= B, IAS_ERR_INVALID,
+              "ias_vicreg_loss_backward: local rows [%d,%d) outside [0,%d)", local_row0, local_row0 + B_local, B);
+  IAS_REQUIRE(B > 1 && cfg_batch_size != 1 && embeddim > 0, IAS_ERR_INVALID,
+              "ias_vicreg_loss_backward: B=%d cfg_batch_size=%d embeddim=%d", B, cfg_batch_size, embeddim);
+  const Plan p = make_plan(B, D);
+  return run_backward(x, y, p, local_row0, B_local, cfg_batch_size, embeddim, sim_coeff, std_coeff, cov_coeff, gout4,
+                      gx, gy, 0, B, 1.0f, reinterpret_cast<float*>(workspace), as_stream(stream));
+}
+
+// ---- fused gather path ---------------------------------------------------------------------------------------------
+extern "C" size_t ias_vicreg_gather_workspace_bytes(int world, int B_local, int D) {
+  if (world <= 0 || B_local <= 0 || D <= 0) return 0;
+  size_t a, b, total;
+  gather_plan(world, B_local, D, &a, &b, &total);
+  return total * sizeof(float);
+}
+
+extern "C" int ias_vicreg_loss_gather(const float* const* x_peers_host, const float* const* y_peers_host, int world,
+                                      int rank, int B_local, int cfg_batch_size, int D, int embeddim, float sim_coeff,
+                                      float std_coeff, float cov_coeff, float* out4, void* workspace,
+                                      size_t workspace_bytes, ias_stream_t stream) {
+  IAS_REQUIRE(x_peers_host && y_peers_host && out4, IAS_ERR_INVALID, "ias_vicreg_loss_gather: NULL pointer");
+  IAS_REQUIRE(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world && B_local > 0 && D > 0, IAS_ERR_INVALID,
+              "ias_vicreg_loss_gather: world=%d rank=%d B_local=%d D=%d (at most %d peers)", world, rank, B_local, D,
+              MAX_PEERS);
+  IAS_REQUIRE(cfg_batch_size != 1 && embeddim > 0, IAS_ERR_INVALID, "ias_vicreg_loss_gather: cfg_batch_size=%d", cfg_batch_size);
+  size_t off_xg, off_yg, total;
+  const Plan p = gather_plan(world, B_local, D, &off_xg, &off_yg, &total);
+  IAS_REQUIRE(workspace && workspace_bytes >= total * sizeof(float), IAS_ERR_WORKSPACE,
+              "ias_vicreg_loss_gather: workspace %zu < %zu bytes", workspace_bytes, total * sizeof(float));
+  IAS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023u) == 0, IAS_ERR_INVALID,
+              "ias_vicreg_loss_gather: workspace must be 1024-byte aligned");
+  RowSrc src;
+  for (int i = 0; i < MAX_PEERS; ++i) src.x[i] = src.y[i] = nullptr;
+  for (int i = 0; i < world; ++i) {
+    IAS_REQUIRE(x_peers_host[i] && y_peers_host[i], IAS_ERR_INVALID, "ias_vicreg_loss_gather: peer %d pointer is NULL", i);
+    src.x[i] = x_peers_host[i];
+    src.y[i] = y_peers_host[i];
+  }
+  src.rows_per = B_local;
+  float* w = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  int rc = run_stats_and_gram(src, w + off_xg, w + off_yg, w + off_xg, w + off_yg, p, rank * B_local, B_local, w,
+                              w + p.off_gfull, st);
+  if (rc) return rc;
+  FinalArgs a;
+  a.repr = w + p.off_repr;
+  a.covp = w + p.off_covp;
+  a.varpart = w + p.off_varpart;
+  a.stats = w + p.off_stats;
+  a.out4 = out4;
+  a.P = p.P;
+  a.ncovp_per_side = p.ntiles * (TILE / 16);
+  a.D = D; a.Dp = p.Dp; a.B = p.B; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
+  a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
+  {
+    ProfScope prof_(K_VICREG_FINALIZE, st);
+    k_finalize<<<1, 256, 0, st>>>(a);
+  }
+  IAS_LAUNCH_CHECK("k_finalize");
+  return IAS_OK;
+}
+
+extern "C" int ias_vicreg_loss_gather_backward(int world, int rank, int B_local, int cfg_batch_size, int D, int embeddim,
+                                               float sim_coeff, float std_coeff, float cov_coeff, const float* gout4,
+                                               float* gx_local, float* gy_local, void* workspace,
+                                               size_t workspace_bytes, ias_stream_t stream) {
+  IAS_REQUIRE(gout4 && gx_local && gy_local, IAS_ERR_INVALID, "ias_vicreg_loss_gather_backward: NULL pointer");
+  IAS_REQUIRE(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world && B_local > 0 && D > 0, IAS_ERR_INVALID,
+              "ias_vicreg_loss_gather_backward: world=%d rank=%d B_local=%d D=%d", world, rank, B_local, D);
+  size_t off_xg, off_yg, total;
+  const Plan p = gather_plan(world, B_local, D, &off_xg, &off_yg, &total);
+  IAS_REQUIRE(workspace && workspace_bytes >= total * sizeof(float), IAS_ERR_WORKSPACE,
+              "ias_vicreg_loss_gather_backward: workspace %zu < %zu bytes", workspace_bytes, total * sizeof(float));
+  IAS_REQUIRE(p.B > 1, IAS_ERR_INVALID, "ias_vicreg_loss_gather_backward: global batch of 1");
+  float* w = reinterpret_cast<float*>(workspace);
+  // Every rank holds the same std/cov terms, so the sum over ranks of their gradients w.r.t. this rank's rows is
+  // `world` times the own-row slice: no reduce-scatter is needed (FullGatherLayer.backward semantics, vicreg.py:92-95).
+  return run_backward(w + off_xg, w + off_yg, p, rank * B_local, B_local, cfg_batch_size, embeddim, sim_coeff, std_coeff,
+                      cov_coeff, gout4, gx_local, gy_local, rank * B_local, B_local, (float)world, w, as_stream(stream));
 }

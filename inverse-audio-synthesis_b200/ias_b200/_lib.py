@@ -74,6 +74,17 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p,
          c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "ias_vicreg_gather_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "ias_vicreg_loss_gather": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p,
+         c_size_t, c_void_p],
+    ),
+    "ias_vicreg_loss_gather_backward": (
+        c_int,
+        [c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+         c_size_t, c_void_p],
+    ),
     "ias_vicreg_gram_reference": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ias_vicreg_gram_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ias_abs_avg_pool": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_longlong, c_int, c_void_p]),

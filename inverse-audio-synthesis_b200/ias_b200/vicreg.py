@@ -146,6 +146,13 @@ def vicreg_loss(x, y, cfg_batch_size: int, embeddim: int, sim_coeff: float, std_
     rank, world = _world()
     b_local = x.shape[0]
     if gather and world > 1:
+        from . import dist as ias_dist
+
+        ex = ias_dist.fused_exchange()
+        if ex is not None:
+            return ias_dist.FusedGatherLoss.apply(x, y, ex, int(cfg_batch_size), int(embeddim), float(sim_coeff),
+                                                  float(std_coeff), float(cov_coeff))
+    if gather and world > 1:
         x_all = torch.cat(FullGatherLayer.apply(x), dim=0)
         y_all = torch.cat(FullGatherLayer.apply(y), dim=0)
         row0 = rank * b_local

@@ -53,6 +53,29 @@ def main():
             print(f"{'PASS' if good else 'FAIL'} reduce_scatter via libias_comm: {own.flatten()[0].item()} == {expect}")
         ok = ok and good
         ias_b200.use_communicator(None)
+    # fused gather: the statistics kernel reads every rank's embeddings over NVLink itself (no collective launch)
+    ex = ias_b200.EmbeddingExchange(B_local, D, dev)
+    ias_b200.use_fused_gather(ex)
+    for it in range(3):  # several rounds: exercises the reuse barriers of the exchange buffer
+        xs = (x_all[sl] * (1.0 + 0.25 * it)).to(dev).requires_grad_(True)
+        ys = (y_all[sl] - 0.5 * it).to(dev).requires_grad_(True)
+        out = ias_b200.vicreg_loss(xs, ys, world * B_local, D, 25.0, 25.0, 1.0)
+        out[0].backward()
+        xa, ya = (x_all * (1.0 + 0.25 * it)).numpy(), (y_all - 0.5 * it).numpy()
+        want_it = np.array(OV.loss(xa, ya, world * B_local, D, local_rows=sl))
+        got = np.array([float(o) for o in out])
+        gx_full, gy_full = OV.loss_grad(xa, ya, world * B_local, D)  # grads of the single-process loss
+        # sum over ranks of d L_r / d x_own = world * (single-process gradient) on the own rows (see test_dist_gloo)
+        egx = np.abs(xs.grad.cpu().numpy() - world * gx_full[sl]).max() / np.abs(world * gx_full[sl]).max()
+        egy = np.abs(ys.grad.cpu().numpy() - world * gy_full[sl]).max() / np.abs(world * gy_full[sl]).max()
+        rel = np.abs(got - want_it) / np.abs(want_it)
+        good = bool(np.all(rel <= 1e-4)) and egx <= 1e-4 and egy <= 1e-4
+        flags = torch.tensor([1 if good else 0], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"{'PASS' if flags.item() else 'FAIL'} fused gather round {it}: rel {rel} grad rel {egx:.2e} {egy:.2e}")
+        ok = ok and bool(flags.item())
+    ias_b200.use_fused_gather(None)
     # sharded front end: this rank's sounds equal the same ids rendered by a single process
     cfg = ias_b200.SynthConfig(batch_size=64, reproducible=True, buffer_size_seconds=0.5)
     voice = ias_b200.Voice(cfg).to(dev)
