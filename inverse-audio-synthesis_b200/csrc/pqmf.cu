@@ -82,6 +82,32 @@ __device__ __forceinline__ void stage_row(float* __restrict__ dst, const float* 
   }
 }
 
+// Interior tiles (every float4 group inside the row, 16-byte aligned, no gain): all global loads are issued before
+// the first shared store, no bounds logic.  `src` points at global index g0 of the row.
+template <int S, int SPAN4>
+__device__ __forceinline__ void stage_row_interior(float* __restrict__ dst, const float* __restrict__ src) {
+  using P = Pad<S>;
+  constexpr int ITERS = (SPAN4 + PQ_THREADS - 1) / PQ_THREADS;
+  const float4* s4 = reinterpret_cast<const float4*>(src) + threadIdx.x;
+  float4 v[ITERS];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i)
+    if ((i + 1) * PQ_THREADS <= SPAN4 || (int)threadIdx.x + i * PQ_THREADS < SPAN4) v[i] = __ldg(s4 + i * PQ_THREADS);
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i)
+    if ((i + 1) * PQ_THREADS <= SPAN4 || (int)threadIdx.x + i * PQ_THREADS < SPAN4) {
+      const int i4 = (int)threadIdx.x + i * PQ_THREADS;
+      if constexpr (P::VEC) {
+        *reinterpret_cast<float4*>(dst + P::at(4 * i4)) = v[i];
+      } else {
+        dst[P::at(4 * i4 + 0)] = v[i].x;
+        dst[P::at(4 * i4 + 1)] = v[i].y;
+        dst[P::at(4 * i4 + 2)] = v[i].z;
+        dst[P::at(4 * i4 + 3)] = v[i].w;
+      }
+    }
+}
+
 // Sliding window of this thread: linear floats [t*S + OFF, t*S + OFF + WIN) of the staged row -> registers.
 template <int S, int OFF, int WIN>
 __device__ __forceinline__ void load_window(const float* __restrict__ src, float (&w)[WIN]) {
@@ -127,7 +153,11 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   const float scale = row_scale ? row_scale[b] : 1.0f;
   const int g0 = n_tile * N - PAD - OFF;  // multiple of 4
   const bool vec_ok = ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
-  stage_row<S, SPAN4>(xs, x + (size_t)b * T, g0, T, scale, vec_ok);
+  // the per-row gain is applied to the accumulators (linear), so the staged samples are the raw input
+  if (vec_ok && g0 >= 0 && g0 + 4 * SPAN4 <= T)
+    stage_row_interior<S, SPAN4>(xs, x + (size_t)b * T + g0);
+  else
+    stage_row<S, SPAN4>(xs, x + (size_t)b * T, g0, T, 1.0f, vec_ok);
   __syncthreads();
 
   float w[WIN];
@@ -163,6 +193,13 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
       for (int k = 0; k < N; ++k)
 #pragma unroll
         for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.c[k * 2 * N + r], ps[q][r], acc[q][k]);
+  }
+
+  if (row_scale) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[q][k] *= scale;
   }
 
   const int n0 = n_tile + threadIdx.x * Q;

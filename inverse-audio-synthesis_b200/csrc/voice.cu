@@ -123,6 +123,7 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 // k_voice_control
 // ------------------------------------------------------------------------------------------------------------
 constexpr int CTRL_THREADS = 256;
+constexpr int REC_FLOATS = 16;  // floats per control-interval record (4 x 16-byte loads in the audio stage)
 
 struct ControlShared {
   float P[NROWS];
@@ -133,9 +134,16 @@ struct ControlShared {
   int last_nz[CTRL_THREADS / 32];
 };
 
+// Per-interval record j of one voice, read by the audio-stage threads whose samples start in control interval j:
+//   [0..2]  vco_1_pitch at points j, j+1, j+2 (clamped to C-1)      exact values: they feed the phase
+//   [3..5]  vco_2_pitch at points j, j+1, j+2
+//   [6..8]  AmpLine of vco_1_amp  * mixer level 1
+//   [9..11] AmpLine of vco_2_amp  * mixer level 2 * (1 - shape/2)
+//   [12..14] AmpLine of noise_amp * mixer level 3
 __global__ void __launch_bounds__(CTRL_THREADS)
 k_voice_control(const float* __restrict__ params01, int B, int C, float cr, float eps, RangeTable ranges,
-                float* __restrict__ ctrl, float* __restrict__ scratch, float* __restrict__ vconst) {
+                const float* __restrict__ ctrl_in, float* __restrict__ ctrl, float* __restrict__ scratch,
+                float* __restrict__ vconst, float4* __restrict__ rec) {
   __shared__ ControlShared sh;
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -200,18 +208,38 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
 
   // Phase C: LFO shapes, VCAs, modulation matrix
   float* out = ctrl + (size_t)b * IAS_VOICE_NCONTROL * C;
-  int last_nz = -1;  // last control point where any amplitude signal (vco_1_amp, vco_2_amp, noise_amp) is non-zero
   for (int j = tid; j < C; j += CTRL_THREADS) {
     float l1 = mul(lfo_shapes_mix(sh.lfo[0], sc[0 * C + j]), sc[2 * C + j]);
     float l2 = mul(lfo_shapes_mix(sh.lfo[1], sc[1 * C + j]), sc[3 * C + j]);
     float a1 = sc[4 * C + j], a2 = sc[5 * C + j];
-    float o5[5];
 #pragma unroll
-    for (int o = 0; o < 5; ++o) {
-      o5[o] = modmatrix_out(sh.mm, o, a1, a2, l1, l2);
-      out[o * C + j] = o5[o];
-    }
-    if (o5[1] != 0.0f || o5[3] != 0.0f || o5[4] != 0.0f) last_nz = j;
+    for (int o = 0; o < 5; ++o) out[o * C + j] = modmatrix_out(sh.mm, o, a1, a2, l1, l2);
+  }
+  __syncthreads();  // this CTA's ctrl rows are re-read below
+
+  // Phase D: per-interval records for the audio stage (from the caller's signals when the parity hook supplies them)
+  const float* src = ctrl_in ? ctrl_in + (size_t)b * IAS_VOICE_NCONTROL * C : out;
+  const float shape = sh.P[VCO2 + 3];
+  const float lev1 = sh.P[MIX + 0];
+  const float lev2 = mul(sh.P[MIX + 1], sub(1.0f, mul(shape, 0.5f)));
+  const float lev3 = sh.P[MIX + 2];
+  float4* rv = rec + (size_t)b * C * (REC_FLOATS / 4);
+  int last_nz = -1;  // last control point where any amplitude signal (vco_1_amp, vco_2_amp, noise_amp) is non-zero
+  for (int j = tid; j < C; j += CTRL_THREADS) {
+    const int ja = min(j + 1, C - 1), jb = min(j + 2, C - 1);
+    const float* s0 = src + 0 * C;
+    const float* s1 = src + 1 * C;
+    const float* s2 = src + 2 * C;
+    const float* s3 = src + 3 * C;
+    const float* s4 = src + 4 * C;
+    const AmpLine g1 = amp_line(s1[j], s1[ja], s1[jb], lev1);
+    const AmpLine g2 = amp_line(s3[j], s3[ja], s3[jb], lev2);
+    const AmpLine g3 = amp_line(s4[j], s4[ja], s4[jb], lev3);
+    rv[j * 4 + 0] = make_float4(s0[j], s0[ja], s0[jb], s2[j]);
+    rv[j * 4 + 1] = make_float4(s2[ja], s2[jb], g1.c0, g1.d0);
+    rv[j * 4 + 2] = make_float4(g1.dd, g2.c0, g2.d0, g2.dd);
+    rv[j * 4 + 3] = make_float4(g3.c0, g3.d0, g3.dd, 0.0f);
+    if (s1[j] != 0.0f || s3[j] != 0.0f || s4[j] != 0.0f) last_nz = j;
   }
   // Envelopes end in exact zeros (pow(0, alpha) == 0 after the release): tell the audio stage where the silent tail
   // starts so it can write zeros instead of rendering oscillators that are multiplied by 0.
@@ -227,17 +255,68 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// k_voice_schedule: live tile count per voice and the order the audio CTAs pull voices in (longest first), so that
+// the SMs finish together although voices differ in length (note duration + release) by two orders of magnitude.
+// One CTA; counting sort on the live tile count.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SCHED_THREADS = 1024;
+constexpr int SCHED_BINS = 2048;
+
+__global__ void __launch_bounds__(SCHED_THREADS)
+k_voice_schedule(const float* __restrict__ vconst, int B, int T, float scale, int tile, int render_all,
+                 int* __restrict__ ntiles, int* __restrict__ order, int* __restrict__ counter) {
+  __shared__ int s_bin[SCHED_BINS];
+  __shared__ int s_wtot[SCHED_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int all = (T + tile - 1) / tile;
+  for (int i = tid; i < SCHED_BINS; i += SCHED_THREADS) s_bin[i] = 0;
+  if (tid == 0) *counter = 0;
+  __syncthreads();
+  // Samples whose control interval [i0, i0+1] lies wholly in the silent tail are exactly 0 (every VCA gain is 0):
+  // only the tiles before the first tile that starts inside the tail are rendered.
+  auto starts_silent = [&](int t, int silent_from) { return (int)mul(scale, (float)(t * tile)) >= silent_from; };
+  auto key_of = [&](int nt) { return (SCHED_BINS - 1) - (int)(((long long)nt * (SCHED_BINS - 1)) / all); };  // long first
+  for (int v = tid; v < B; v += SCHED_THREADS) {
+    int nt = all;
+    if (!render_all) {
+      const int silent_from = (int)fminf(vconst[(size_t)v * VC_COUNT + VC_SILENT_FROM], 1e9f);
+      int t = min(all, (int)((float)silent_from / (scale * (float)tile)));
+      while (t > 0 && starts_silent(t - 1, silent_from)) --t;
+      while (t < all && !starts_silent(t, silent_from)) ++t;
+      nt = t;
+    }
+    ntiles[v] = nt;
+    atomicAdd(&s_bin[key_of(nt)], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the bins (2 per thread)
+  const int c0 = s_bin[2 * tid], c1 = s_bin[2 * tid + 1];
+  int inc = c0 + c1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_wtot[warp] = inc;
+  __syncthreads();
+  int base = inc - (c0 + c1);
+  for (int w = 0; w < warp; ++w) base += s_wtot[w];
+  s_bin[2 * tid] = base;
+  s_bin[2 * tid + 1] = base + c0;
+  __syncthreads();
+  for (int v = tid; v < B; v += SCHED_THREADS) order[atomicAdd(&s_bin[key_of(ntiles[v])], 1)] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // k_voice_audio
 // ------------------------------------------------------------------------------------------------------------
-constexpr int AUD_THREADS = 128;
-constexpr int AUD_SPT = 8;  // samples per thread per tile
-constexpr int AUD_TILE = AUD_THREADS * AUD_SPT;
-constexpr int AUD_WARPS = AUD_THREADS / 32;
-
 struct AudioArgs {
-  const float* ctrl;    // [B][5][C]
+  const float4* rec;    // [B][C][4] per-interval records (k_voice_control)
   const float* vconst;  // [B][16]
   const float* noise;   // [R][T]
+  const int* ntiles;    // [B] live tiles of each voice (k_voice_schedule)
+  const int* order;     // [B] voice ids, longest first
+  int* counter;         // work queue head
   float* audio;         // [B][T]
   float* peak;          // [B] or null
   float* phase_dbg;     // [B][2][T] or null
@@ -245,235 +324,302 @@ struct AudioArgs {
   float scale;          // float(C-1)/float(T-1)
   float sr, rsr;
   int normalize;
-  int ctrl_overridden;  // ctrl comes from the caller (parity hook): the silent-tail marker does not describe it
 };
 
-// control values of signal `sig` at points j, j+1, j+2 (clamped), for a thread whose 8 samples start in interval j
-struct Ctl3 {
-  float v0, v1, v2;
-};
-__device__ __forceinline__ Ctl3 load_ctl(const float* __restrict__ row, int j, int C) {
-  Ctl3 c;
-  c.v0 = __ldg(row + min(j, C - 1));
-  c.v1 = __ldg(row + min(j + 1, C - 1));
-  c.v2 = __ldg(row + min(j + 2, C - 1));
-  return c;
-}
-__device__ __noinline__ int live_tiles(int T, float scale, float silent_from_f) {
-  const int all = (T + AUD_TILE - 1) / AUD_TILE;
-  const int silent_from = (int)fminf(silent_from_f, 1e9f);
-  for (int t = 0; t < all; ++t)
-    if ((int)mul(scale, (float)(t * AUD_TILE)) >= silent_from) return t;
-  return all;
-}
-
-template <bool VEC, bool DBG>
-__global__ void __launch_bounds__(AUD_THREADS, 7) k_voice_audio(AudioArgs A) {
-  __shared__ double s_wsum[2][2][AUD_WARPS];  // [buffer][vco][warp]
-  __shared__ float s_peak[AUD_WARPS];
-  const int b = blockIdx.x;
+// Persistent CTAs pull voices from the queue.  Per voice: tiles of NT*SPT samples, SPT consecutive samples per thread.
+//   pass 1  pitch path of both VCOs, bit for bit the reference's fp32 op sequence -> phase increments x1, x2
+//   scan    fp64 block scan of the increments (exact for 4 s clips), carry across tiles
+//   pass 2  oscillators, VCA gains (AmpLine), noise, mix, running peak
+template <int NT, int SPT, int MINB, bool VEC, bool DBG>
+__global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
+  constexpr int TILE = NT * SPT;
+  constexpr int NW = NT / 32;
+  __shared__ double s_wsum[2][2][NW];  // [buffer][vco][warp]
+  __shared__ float s_peak[NW];
+  __shared__ int s_slot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = A.T, C = A.C;
-  const float* vc = A.vconst + (size_t)b * VC_COUNT;
-  const float midi1 = vc[VC_MIDI1], depth1 = vc[VC_DEPTH1], phase1 = vc[VC_PHASE1];
-  const float midi2 = vc[VC_MIDI2], depth2 = vc[VC_DEPTH2], phase2 = vc[VC_PHASE2];
-  const float pk = vc[VC_PK], shape = vc[VC_SHAPE], gain2 = vc[VC_GAIN2];
-  const float lev1 = vc[VC_LEVEL1], lev2 = vc[VC_LEVEL2], lev3 = vc[VC_LEVEL3];
-  const float* ctl = A.ctrl + (size_t)b * IAS_VOICE_NCONTROL * C;
-  const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
-  float* out = A.audio + (size_t)b * T;
   const float scale = A.scale;
-  // Samples whose control interval [i0, i0+1] lies wholly in the silent tail are exactly 0 (every VCA gain is 0):
-  // render only the tiles before the first tile that starts inside the tail, zero-fill the rest.
-  const int ntiles = live_tiles(T, scale, A.ctrl_overridden ? 1e30f : vc[VC_SILENT_FROM]);
 
-  double carry1 = 0.0, carry2 = 0.0;
-  float tpeak = 0.0f;
-  float ft0 = (float)(tid * AUD_SPT);  // float(index of the thread's first sample); exact, advanced by AUD_TILE per tile
-  for (int tile = 0; tile < ntiles; ++tile, ft0 += (float)AUD_TILE) {
-    const int t0 = tile * AUD_TILE + tid * AUD_SPT;
-    const int buf = tile & 1;
-    // control interval of the thread's first sample (its 8 samples touch intervals j and j+1 only)
-    const int j = min((int)mul(scale, fminf(ft0, (float)(T - 1))), C - 1);
-    const float fj = (float)j;
-    // ---- pass 1: phase increments of both VCOs -----------------------------------------------------------
-    float x1[AUD_SPT], x2[AUD_SPT];
-    {
-      const Ctl3 p1 = load_ctl(ctl + 0 * C, j, C);
-      const Ctl3 p2 = load_ctl(ctl + 2 * C, j, C);
+  for (;;) {
+    if (tid == 0) s_slot = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot >= A.B) break;
+    const int b = A.order[slot];
+    const float* vc = A.vconst + (size_t)b * VC_COUNT;
+    const float midi1 = vc[VC_MIDI1], depth1 = vc[VC_DEPTH1], phase1 = vc[VC_PHASE1];
+    const float midi2 = vc[VC_MIDI2], depth2 = vc[VC_DEPTH2], phase2 = vc[VC_PHASE2];
+    const float pk = vc[VC_PK], shape = vc[VC_SHAPE];
+    const float4* rec = A.rec + (size_t)b * C * (REC_FLOATS / 4);
+    const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
+    float* out = A.audio + (size_t)b * T;
+    const int ntiles = A.ntiles[b];
+
+    double carry1 = 0.0, carry2 = 0.0;
+    float tpeak = 0.0f;
+    float ft0 = (float)(tid * SPT);  // float(index of the thread's first sample); exact, advanced by TILE per tile
+    for (int tile = 0; tile < ntiles; ++tile, ft0 += (float)TILE) {
+      const int t0 = tile * TILE + tid * SPT;
+      const int buf = tile & 1;
+      // control interval of the thread's first sample (its SPT samples touch intervals j and j+1 only)
+      const int j = min((int)mul(scale, fminf(ft0, (float)(T - 1))), C - 1);
+      const float fj = (float)j;
+      const float fj1 = add(fj, 1.0f);
+      const float4* rj = rec + (size_t)j * 4;
+      // ---- pass 1: phase increments of both VCOs ---------------------------------------------------------
+      float x1[SPT], x2[SPT], srcs[SPT];
+      const float4 r0 = __ldg(rj + 0);
+      const float4 r1 = __ldg(rj + 1);
 #pragma unroll
-      for (int k = 0; k < AUD_SPT; ++k) {
-        float l0, l1;
-        const bool d = upsample_coords_f(ft0 + (float)k, scale, fj, l0, l1);
-        const float m1 = upsample_mix(d ? p1.v1 : p1.v0, d ? p1.v2 : p1.v1, l0, l1);
-        const float m2 = upsample_mix(d ? p2.v1 : p2.v0, d ? p2.v2 : p2.v1, l0, l1);
-        // VEC: T % 8 == 0, so a thread is wholly live or wholly past the end; dead threads sit after every live
+      for (int k = 0; k < SPT; ++k) {
+        const float src = mul(scale, add(ft0, (float)k));  // the reference's fp32 source coordinate
+        srcs[k] = src;
+        const bool d = src >= fj1;
+        const float l1 = sub(src, d ? fj1 : fj);  // in [0,1): j = floor(src) of the thread's first sample
+        const float l0 = sub(1.0f, l1);
+        const float m1 = upsample_mix(d ? r0.y : r0.x, d ? r0.z : r0.y, l0, l1);
+        const float m2 = upsample_mix(d ? r1.x : r0.w, d ? r1.y : r1.x, l0, l1);
+        // VEC: T % SPT == 0, so a thread is wholly live or wholly past the end; dead threads sit after every live
         // one in the last tile, and an inclusive scan never feeds later totals into earlier lanes -> no masking.
         const bool live = VEC || (t0 + k) < T;
         x1[k] = live ? vco_increment(midi1, depth1, m1, A.sr, A.rsr) : 0.0f;
         x2[k] = live ? vco_increment(midi2, depth2, m2, A.sr, A.rsr) : 0.0f;
       }
-    }
-    // ---- block scan (fp64; exact for 4 s clips) -----------------------------------------------
-    double tot1 = 0.0, tot2 = 0.0;
+      // ---- block scan -------------------------------------------------------------------------------------
+      double tot1 = 0.0, tot2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < AUD_SPT; ++k) {
-      tot1 += (double)x1[k];
-      tot2 += (double)x2[k];
-    }
-    const double inc1 = warp_incl_scan(tot1, lane);
-    const double inc2 = warp_incl_scan(tot2, lane);
-    if (lane == 31) {
-      s_wsum[buf][0][warp] = inc1;
-      s_wsum[buf][1][warp] = inc2;
-    }
-    // loads of pass 2 issued before the barrier so their latency overlaps it
-    float nzv[AUD_SPT];
-    if (VEC) {
-      if (t0 < T) {  // T % 8 == 0 on this path: whole groups only
-        const float4 n0 = __ldg(reinterpret_cast<const float4*>(nz + t0));
-        const float4 n1 = __ldg(reinterpret_cast<const float4*>(nz + t0 + 4));
-        nzv[0] = n0.x; nzv[1] = n0.y; nzv[2] = n0.z; nzv[3] = n0.w;
-        nzv[4] = n1.x; nzv[5] = n1.y; nzv[6] = n1.z; nzv[7] = n1.w;
+      for (int k = 0; k < SPT; ++k) {
+        tot1 += (double)x1[k];
+        tot2 += (double)x2[k];
+      }
+      const double inc1 = warp_incl_scan(tot1, lane);
+      const double inc2 = warp_incl_scan(tot2, lane);
+      if (lane == 31) {
+        s_wsum[buf][0][warp] = inc1;
+        s_wsum[buf][1][warp] = inc2;
+      }
+      // loads of pass 2 issued before the barrier so their latency overlaps it
+      const float4 r2 = __ldg(rj + 2);
+      const float4 r3 = __ldg(rj + 3);
+      float nzv[SPT];
+      if (VEC) {
+        if (t0 < T) {
+#pragma unroll
+          for (int q = 0; q < SPT / 4; ++q) {
+            const float4 n4 = __ldg(reinterpret_cast<const float4*>(nz + t0) + q);
+            nzv[4 * q + 0] = n4.x; nzv[4 * q + 1] = n4.y; nzv[4 * q + 2] = n4.z; nzv[4 * q + 3] = n4.w;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < SPT; ++k) nzv[k] = 0.0f;
+        }
       } else {
 #pragma unroll
-        for (int k = 0; k < AUD_SPT; ++k) nzv[k] = 0.0f;
+        for (int k = 0; k < SPT; ++k) nzv[k] = (t0 + k) < T ? __ldg(nz + t0 + k) : 0.0f;
       }
-    } else {
+      __syncthreads();
+      double acc1 = carry1 + (inc1 - tot1), acc2 = carry2 + (inc2 - tot2);
 #pragma unroll
-      for (int k = 0; k < AUD_SPT; ++k) nzv[k] = (t0 + k) < T ? __ldg(nz + t0 + k) : 0.0f;
-    }
-    const Ctl3 q1 = load_ctl(ctl + 1 * C, j, C);
-    const Ctl3 q2 = load_ctl(ctl + 3 * C, j, C);
-    const Ctl3 q3 = load_ctl(ctl + 4 * C, j, C);
-    __syncthreads();
-    double acc1 = carry1 + (inc1 - tot1), acc2 = carry2 + (inc2 - tot2);
-#pragma unroll
-    for (int w = 0; w < AUD_WARPS; ++w) {
-      const double w1 = s_wsum[buf][0][w], w2 = s_wsum[buf][1][w];
-      if (w < warp) {
-        acc1 += w1;
-        acc2 += w2;
-      }
-      carry1 += w1;
-      carry2 += w2;
-    }
-    // ---- pass 2: oscillators, VCAs, noise, mix ------------------------------------------------------------------
-    float y[AUD_SPT];
-#pragma unroll
-    for (int k = 0; k < AUD_SPT; ++k) {
-      float l0, l1;
-      const bool d = upsample_coords_f(ft0 + (float)k, scale, fj, l0, l1);
-      acc1 += (double)x1[k];
-      acc2 += (double)x2[k];
-      const float arg1 = add((float)acc1, phase1);
-      const float arg2 = add((float)acc2, phase2);
-      const float v1 = mul(cos_arg(arg1), upsample_mix(d ? q1.v1 : q1.v0, d ? q1.v2 : q1.v1, l0, l1));
-      const float v2 = mul(squaresaw(arg2, pk, shape, gain2), upsample_mix(d ? q2.v1 : q2.v0, d ? q2.v2 : q2.v1, l0, l1));
-      const float v3 = mul(nzv[k], upsample_mix(d ? q3.v1 : q3.v0, d ? q3.v2 : q3.v1, l0, l1));
-      y[k] = mix3(lev1, v1, lev2, v2, lev3, v3);
-      if (VEC || (t0 + k) < T) tpeak = fmaxf(tpeak, fabsf(y[k]));
-      if (DBG) {
-        if ((t0 + k) < T) {
-          A.phase_dbg[((size_t)b * 2 + 0) * T + t0 + k] = arg1;
-          A.phase_dbg[((size_t)b * 2 + 1) * T + t0 + k] = arg2;
+      for (int w = 0; w < NW; ++w) {
+        const double w1 = s_wsum[buf][0][w], w2 = s_wsum[buf][1][w];
+        if (w < warp) {
+          acc1 += w1;
+          acc2 += w2;
         }
+        carry1 += w1;
+        carry2 += w2;
       }
-    }
-    if (VEC) {
-      if (t0 < T) {
-        reinterpret_cast<float4*>(out + t0)[0] = make_float4(y[0], y[1], y[2], y[3]);
-        reinterpret_cast<float4*>(out + t0)[1] = make_float4(y[4], y[5], y[6], y[7]);
-      }
-    } else {
+      // ---- pass 2: oscillators, VCA gains, noise, mix --------------------------------------------------------
+      float y[SPT];
 #pragma unroll
-      for (int k = 0; k < AUD_SPT; ++k)
-        if ((t0 + k) < T) out[t0 + k] = y[k];
-    }
-  }
-
-  // ---- silent tail -----------------------------------------------------------------------------------------
-  if (ntiles * AUD_TILE < T) {
-    if (VEC) {
-      float4* o4 = reinterpret_cast<float4*>(out);
-      for (int i = ntiles * (AUD_TILE / 4) + tid; i < T / 4; i += AUD_THREADS) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-      for (int i = ntiles * AUD_TILE + tid; i < T; i += AUD_THREADS) out[i] = 0.0f;
-    }
-    if (DBG) {
-      for (int i = ntiles * AUD_TILE + tid; i < T; i += AUD_THREADS) {
-        A.phase_dbg[((size_t)b * 2 + 0) * T + i] = 0.0f;
-        A.phase_dbg[((size_t)b * 2 + 1) * T + i] = 0.0f;
-      }
-    }
-  }
-
-  // ---- per-voice peak, normalize_if_clipping -------------------------------------------------------------------
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) tpeak = fmaxf(tpeak, __shfl_xor_sync(0xffffffffu, tpeak, d));
-  if (lane == 0) s_peak[warp] = tpeak;
-  __syncthreads();  // also orders this CTA's global stores before the re-read below
-  float pkv = s_peak[0];
-#pragma unroll
-  for (int w = 1; w < AUD_WARPS; ++w) pkv = fmaxf(pkv, s_peak[w]);
-  if (tid == 0 && A.peak) A.peak[b] = pkv;
-  if (A.normalize && pkv > 1.0f) {
-    // x / peak, correctly rounded (Markstein step with r = RN(1/peak)); 4 independent 16-byte loads in flight per
-    // thread so this second pass over the row runs at memory speed instead of one round trip per iteration
-    const float rp = vm::div(1.0f, pkv);
-    if (VEC) {
-      float4* o4 = reinterpret_cast<float4*>(out);
-      const int n4 = T / 4;
-      constexpr int U = 4;
-      for (int base = 0; base < n4; base += U * AUD_THREADS) {
-        float4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = base + u * AUD_THREADS + tid;
-          if (i < n4) v[u] = o4[i];
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = base + u * AUD_THREADS + tid;
-          if (i < n4) {
-            v[u].x = div_const(v[u].x, pkv, rp); v[u].y = div_const(v[u].y, pkv, rp);
-            v[u].z = div_const(v[u].z, pkv, rp); v[u].w = div_const(v[u].w, pkv, rp);
-            o4[i] = v[u];
+      for (int k = 0; k < SPT; ++k) {
+        const float u = sub(srcs[k], fj);
+        const float r = fmaxf(sub(srcs[k], fj1), 0.0f);
+        acc1 += (double)x1[k];
+        acc2 += (double)x2[k];
+        const float arg1 = add((float)acc1, phase1);
+        const float arg2 = add((float)acc2, phase2);
+        const float g1 = fma(r, r2.x, fma(u, r1.w, r1.z));
+        const float g2 = fma(r, r2.w, fma(u, r2.z, r2.y));
+        const float g3 = fma(r, r3.z, fma(u, r3.y, r3.x));
+        y[k] = fma(cos_arg(arg1), g1, fma(squaresaw_core(arg2, pk, shape), g2, mul(nzv[k], g3)));
+        if (VEC || (t0 + k) < T) tpeak = fmaxf(tpeak, fabsf(y[k]));
+        if (DBG) {
+          if ((t0 + k) < T) {
+            A.phase_dbg[((size_t)b * 2 + 0) * T + t0 + k] = arg1;
+            A.phase_dbg[((size_t)b * 2 + 1) * T + t0 + k] = arg2;
           }
         }
       }
-    } else {
-      for (int i = tid; i < T; i += AUD_THREADS) out[i] = div_const(out[i], pkv, rp);
+      if (VEC) {
+        if (t0 < T) {
+#pragma unroll
+          for (int q = 0; q < SPT / 4; ++q)
+            reinterpret_cast<float4*>(out + t0)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < SPT; ++k)
+          if ((t0 + k) < T) out[t0 + k] = y[k];
+      }
     }
+
+    // ---- silent tail ---------------------------------------------------------------------------------------
+    if ((long long)ntiles * TILE < T) {
+      if (VEC) {
+        float4* o4 = reinterpret_cast<float4*>(out);
+        for (int i = ntiles * (TILE / 4) + tid; i < T / 4; i += NT) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int i = ntiles * TILE + tid; i < T; i += NT) out[i] = 0.0f;
+      }
+    }
+
+    // ---- per-voice peak, normalize_if_clipping -----------------------------------------------------------------
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tpeak = fmaxf(tpeak, __shfl_xor_sync(0xffffffffu, tpeak, d));
+    if (lane == 0) s_peak[warp] = tpeak;
+    __syncthreads();  // also orders this CTA's global stores before the re-read below
+    float pkv = s_peak[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) pkv = fmaxf(pkv, s_peak[w]);
+    if (tid == 0 && A.peak) A.peak[b] = pkv;
+    if (A.normalize && pkv > 1.0f) {
+      // x / peak, correctly rounded (Markstein step with r = RN(1/peak)); 4 independent 16-byte loads in flight per
+      // thread so this second pass over the row runs at memory speed instead of one round trip per iteration
+      const float rp = vm::div(1.0f, pkv);
+      const int live = min(T, ntiles * TILE);  // the silent tail stays 0
+      if (VEC) {
+        float4* o4 = reinterpret_cast<float4*>(out);
+        const int n4 = live / 4;
+        constexpr int U = 4;
+        for (int base = 0; base < n4; base += U * NT) {
+          float4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = base + u * NT + tid;
+            if (i < n4) v[u] = o4[i];
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = base + u * NT + tid;
+            if (i < n4) {
+              v[u].x = div_const(v[u].x, pkv, rp); v[u].y = div_const(v[u].y, pkv, rp);
+              v[u].z = div_const(v[u].z, pkv, rp); v[u].w = div_const(v[u].w, pkv, rp);
+              o4[i] = v[u];
+            }
+          }
+        }
+      } else {
+        for (int i = tid; i < live; i += NT) out[i] = div_const(out[i], pkv, rp);
+      }
+    }
+    // the barrier above separates this iteration's read of s_slot from the next iteration's write
   }
 }
 
 struct VoiceWorkspace {
+  float4* rec;
   float* ctrl;
   float* scratch;
   float* vconst;
+  int* ntiles;
+  int* order;
+  int* counter;
 };
 
 size_t workspace_floats(int B, int C) {
-  return (size_t)B * IAS_VOICE_NCONTROL * C + (size_t)B * 6 * C + (size_t)B * VC_COUNT;
+  return (size_t)B * C * REC_FLOATS + (size_t)B * IAS_VOICE_NCONTROL * C + (size_t)B * 6 * C + (size_t)B * VC_COUNT +
+         2 * (size_t)B + 4;
 }
 
 VoiceWorkspace carve(void* ws, int B, int C) {
   VoiceWorkspace w;
-  w.ctrl = reinterpret_cast<float*>(ws);
+  float* f = reinterpret_cast<float*>(ws);
+  w.rec = reinterpret_cast<float4*>(f);
+  w.ctrl = f + (size_t)B * C * REC_FLOATS;
   w.scratch = w.ctrl + (size_t)B * IAS_VOICE_NCONTROL * C;
   w.vconst = w.scratch + (size_t)B * 6 * C;
+  w.ntiles = reinterpret_cast<int*>(w.vconst + (size_t)B * VC_COUNT);
+  w.order = w.ntiles + B;
+  w.counter = w.order + B;
   return w;
 }
 
-int launch_control(const float* params01, int B, int C, float cr, float eps, const VoiceWorkspace& w,
-                   cudaStream_t st) {
+int launch_control(const float* params01, int B, int C, float cr, float eps, const float* ctrl_in,
+                   const VoiceWorkspace& w, cudaStream_t st) {
   static const RangeTable ranges = make_range_table();
   {
     ProfScope prof_(K_VOICE_CONTROL, st);
-    k_voice_control<<<B, CTRL_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, w.ctrl, w.scratch, w.vconst);
+    k_voice_control<<<B, CTRL_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, ctrl_in, w.ctrl, w.scratch, w.vconst,
+                                                w.rec);
   }
   IAS_LAUNCH_CHECK("k_voice_control");
+  return IAS_OK;
+}
+
+int sm_count() {
+  static const int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+// Shape of the audio kernel: threads per CTA, samples per thread per tile, resident CTAs per SM.
+struct AudioShape {
+  int nt, spt, ctas_per_sm;
+};
+
+template <int NT, int SPT, int MINB>
+int launch_audio_shape(const AudioArgs& a, bool vec, bool dbg, cudaStream_t st) {
+  const int grid = std::min(a.B, sm_count() * MINB);
+  ProfScope prof_(K_VOICE_AUDIO, st);
+  if (vec && !dbg)
+    k_voice_audio<NT, SPT, MINB, true, false><<<grid, NT, 0, st>>>(a);
+  else if (vec)
+    k_voice_audio<NT, SPT, MINB, true, true><<<grid, NT, 0, st>>>(a);
+  else if (!dbg)
+    k_voice_audio<NT, SPT, MINB, false, false><<<grid, NT, 0, st>>>(a);
+  else
+    k_voice_audio<NT, SPT, MINB, false, true><<<grid, NT, 0, st>>>(a);
+  return IAS_OK;
+}
+
+// IAS_VOICE_SHAPE=<threads>x<samples per thread>x<CTAs per SM> overrides the default shape (tuning runs only).
+// Measured on B200 (profiles/r01f sweep, 1024 x 4 s): 128x16x4 0.84 ms, 256x16x2 0.86, 128x16x3 0.87, 256x8x3 0.93,
+// 128x8x6 0.95, 128x8x7 1.02.  16 samples per thread halve the per-tile scan/barrier cost; it needs T % 16 == 0 for
+// the 128-bit path (4 s: yes; 30 s: T % 8 == 0 only).
+AudioShape pick_shape(int T) {
+  AudioShape s = (T % 16 == 0) ? AudioShape{128, 16, 4} : AudioShape{128, 8, 6};
+  if (const char* e = getenv("IAS_VOICE_SHAPE")) {
+    int nt = 0, spt = 0, c = 0;
+    if (sscanf(e, "%dx%dx%d", &nt, &spt, &c) == 3) s = AudioShape{nt, spt, c};
+  }
+  return s;
+}
+
+int launch_audio(const AudioArgs& a, const VoiceWorkspace& w, bool dbg, cudaStream_t st) {
+  const AudioShape s = pick_shape(a.T);
+  const bool vec = (a.T % s.spt == 0) && ias_aligned16(a.noise) && ias_aligned16(a.audio);
+  {
+    ProfScope prof_(K_VOICE_SCHEDULE, st);
+    k_voice_schedule<<<1, SCHED_THREADS, 0, st>>>(a.vconst, a.B, a.T, a.scale, s.nt * s.spt, dbg ? 1 : 0, w.ntiles,
+                                                  w.order, w.counter);
+  }
+  IAS_LAUNCH_CHECK("k_voice_schedule");
+#define IAS_SHAPE(NT, SPT, MINB) \
+  if (s.nt == NT && s.spt == SPT && s.ctas_per_sm == MINB) { launch_audio_shape<NT, SPT, MINB>(a, vec, dbg, st); } else
+  IAS_SHAPE(128, 8, 7)
+  IAS_SHAPE(128, 8, 6)
+  IAS_SHAPE(128, 16, 4)
+  IAS_SHAPE(128, 16, 3)
+  IAS_SHAPE(256, 8, 3)
+  IAS_SHAPE(256, 16, 2)
+  return set_err(IAS_ERR_UNSUPPORTED, "ias_voice_render: no audio kernel of shape %dx%dx%d", s.nt, s.spt, s.ctas_per_sm);
+#undef IAS_SHAPE
+  IAS_LAUNCH_CHECK("k_voice_audio");
   return IAS_OK;
 }
 
@@ -522,8 +668,9 @@ extern "C" int ias_voice_control(const float* params01, int B, int C, float cont
   IAS_REQUIRE(params01 && ctrl, IAS_ERR_INVALID, "ias_voice_control: NULL pointer");
   IAS_REQUIRE(workspace && workspace_bytes >= ias_voice_workspace_bytes(B, 0, C), IAS_ERR_WORKSPACE,
               "ias_voice_control: workspace %zu < %zu bytes", workspace_bytes, ias_voice_workspace_bytes(B, 0, C));
+  IAS_REQUIRE(ias_aligned16(workspace), IAS_ERR_INVALID, "ias_voice_control: workspace must be 16-byte aligned");
   VoiceWorkspace w = carve(workspace, B, C);
-  int rc = launch_control(params01, B, C, control_rate, eps, w, as_stream(stream));
+  int rc = launch_control(params01, B, C, control_rate, eps, nullptr, w, as_stream(stream));
   if (rc) return rc;
   IAS_CUDA(cudaMemcpyAsync(ctrl, w.ctrl, (size_t)B * IAS_VOICE_NCONTROL * C * sizeof(float),
                            cudaMemcpyDeviceToDevice, as_stream(stream)));
@@ -537,20 +684,24 @@ extern "C" int ias_voice_render(const float* params01, const float* noise, int n
   IAS_REQUIRE(B > 0 && T > 1 && C > 1 && noise_rows > 0, IAS_ERR_INVALID, "ias_voice_render: B=%d T=%d C=%d R=%d", B,
               T, C, noise_rows);
   IAS_REQUIRE(T < (1 << 24), IAS_ERR_UNSUPPORTED, "ias_voice_render: T=%d exceeds 2^24 samples", T);
-  IAS_REQUIRE((long long)(T - 1) >= (long long)AUD_SPT * (C - 1), IAS_ERR_UNSUPPORTED,
-              "ias_voice_render: needs at least %d audio samples per control sample (T=%d C=%d)", AUD_SPT, T, C);
+  IAS_REQUIRE((long long)(T - 1) >= 16ll * (C - 1), IAS_ERR_UNSUPPORTED,
+              "ias_voice_render: needs at least %d audio samples per control sample (T=%d C=%d)", 16, T, C);
   IAS_REQUIRE(params01 && noise && audio, IAS_ERR_INVALID, "ias_voice_render: NULL pointer");
   IAS_REQUIRE(sample_rate > 0.f && control_rate > 0.f, IAS_ERR_INVALID, "ias_voice_render: rates must be positive");
   IAS_REQUIRE(workspace && workspace_bytes >= ias_voice_workspace_bytes(B, T, C), IAS_ERR_WORKSPACE,
               "ias_voice_render: workspace %zu < %zu bytes", workspace_bytes, ias_voice_workspace_bytes(B, T, C));
+  IAS_REQUIRE(ias_aligned16(workspace), IAS_ERR_INVALID, "ias_voice_render: workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   VoiceWorkspace w = carve(workspace, B, C);
-  int rc = launch_control(params01, B, C, control_rate, eps, w, st);
+  int rc = launch_control(params01, B, C, control_rate, eps, ctrl_in, w, st);
   if (rc) return rc;
   AudioArgs a;
-  a.ctrl = ctrl_in ? ctrl_in : w.ctrl;
+  a.rec = w.rec;
   a.vconst = w.vconst;
   a.noise = noise;
+  a.ntiles = w.ntiles;
+  a.order = w.order;
+  a.counter = w.counter;
   a.audio = audio;
   a.peak = peak;
   a.phase_dbg = phase_dbg;
@@ -559,19 +710,5 @@ extern "C" int ias_voice_render(const float* params01, const float* noise, int n
   a.sr = sample_rate;
   a.rsr = 1.0f / sample_rate;
   a.normalize = normalize;
-  a.ctrl_overridden = ctrl_in != nullptr;
-  const bool vec = (T % 8 == 0) && ias_aligned16(noise) && ias_aligned16(audio);
-  {
-    ProfScope prof_(K_VOICE_AUDIO, st);
-    if (vec && !phase_dbg)
-      k_voice_audio<true, false><<<B, AUD_THREADS, 0, st>>>(a);
-    else if (vec)
-      k_voice_audio<true, true><<<B, AUD_THREADS, 0, st>>>(a);
-    else if (!phase_dbg)
-      k_voice_audio<false, false><<<B, AUD_THREADS, 0, st>>>(a);
-    else
-      k_voice_audio<false, true><<<B, AUD_THREADS, 0, st>>>(a);
-  }
-  IAS_LAUNCH_CHECK("k_voice_audio");
-  return IAS_OK;
+  return launch_audio(a, w, phase_dbg != nullptr, st);
 }

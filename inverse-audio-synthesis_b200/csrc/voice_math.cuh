@@ -466,17 +466,17 @@ IAS_HD float vco_increment(float midi, float depth, float mod, float sr, float r
   return div_const(mul(IAS_TWO_PI_F, midi_to_hz(m)), sr, rsr);
 }
 
-// a = (n + f) * pi with f in [-0.5, 0.5]; accurate for |a| < 2^22 * pi.  (error-free product + two-term 1/pi)
+// a = (n + f) * pi with f in [-0.5, 0.5]; accurate for |a| < 2^22 * pi.  n = rint(a * C1) from one FMA against the
+// 1.5 * 2^23 magic constant; the second FMA forms a*C1 - n with a single rounding (relative to the small result, so
+// accuracy near the zeros of sin is kept), the third adds the 1/pi tail.
 IAS_HD void reduce_half_turns(float a, float& f, int& n) {
   const float C1 = 0.318309873342514038f;                                            // (float)(1/pi)
   const float C2 = (float)(0.31830988618379067154 - (double)0.318309873342514038f);  // 1/pi - C1
-  float p = mul(a, C1);
-  float e = fma(a, C1, -p);
   const float magic = 12582912.0f;
-  float t = add(p, magic);
-  n = f2i(t);  // low bit = parity of rint(p)
+  float t = fma(a, C1, magic);
+  n = f2i(t);  // low bit = parity of rint(a/pi)
   float nf = sub(t, magic);
-  f = add(sub(p, nf), fma(a, C2, e));
+  f = fma(a, C2, fma(a, C1, -nf));
 }
 
 // sin(pi*f) for |f| <= 0.5625 (reduce_half_turns can overshoot 0.5 by the ulp of a/pi for 30 s clips): odd degree-9
@@ -535,6 +535,33 @@ IAS_HD float squaresaw(float arg, float pk, float shape, float gain) {
   sincos_arg(arg, s, c);
   float sq = tanh_from_scaled(mul(pk, s));
   return mul(mul(gain, sq), fma(shape, c, 1.0f));
+}
+
+// ---- amplitude path of the audio stage ------------------------------------------------------------------------
+// The three VCA gains (vco_1_amp, vco_2_amp, noise_amp) are linear interpolations of control points j, j+1, j+2 for a
+// thread whose samples start in control interval j.  With u = src - j (src = the reference's fp32 source coordinate,
+// so its quantisation is reproduced) and r = max(u - 1, 0):
+//     gain(u) = v0 + u*(v1 - v0) + r*((v2 - v1) - (v1 - v0))
+// which equals the reference's l0*x[i0] + l1*x[i1] on both sides of the interval boundary up to fp32 rounding
+// (<= 2e-7; amplitude path only, never feeds a phase).  The mixer level (and SquareSawVCO's 1 - shape/2) is folded in.
+struct AmpLine {
+  float c0, d0, dd;
+};
+IAS_HD AmpLine amp_line(float v0, float v1, float v2, float level) {
+  AmpLine a;
+  const float d0 = sub(v1, v0);
+  a.c0 = mul(level, v0);
+  a.d0 = mul(level, d0);
+  a.dd = mul(level, sub(sub(v2, v1), d0));
+  return a;
+}
+IAS_HD float amp_eval(const AmpLine& a, float u, float r) { return fma(r, a.dd, fma(u, a.d0, a.c0)); }
+
+// SquareSawVCO.oscillator without its constant gain: tanh(pi*k*sin(arg)/2) * (1 + shape*cos(arg))
+IAS_HD float squaresaw_core(float arg, float pk, float shape) {
+  float s, c;
+  sincos_arg(arg, s, c);
+  return mul(tanh_from_scaled(mul(pk, s)), fma(shape, c, 1.0f));
 }
 
 // AudioMixer matmul [1,3]x[3,T]: FMA chain in k order

@@ -53,7 +53,8 @@ def test_library_loads_and_reports_errors(built_lib):
     assert lib.ias_pqmf_out_len(176400, 16, 63) == 11025
     assert lib.ias_pqmf_out_len(1323000, 16, 63) == 82688
     assert lib.ias_pqmf_out_len(1, 3, 63) == 1
-    assert lib.ias_voice_workspace_bytes(1024, 176400, 1764) == 4 * (1024 * 11 * 1764 + 1024 * 16)
+    # records [B][C][16] + ctrl [B][5][C] + scratch [B][6][C] + constants [B][16] + schedule (2B + 4 ints)
+    assert lib.ias_voice_workspace_bytes(1024, 176400, 1764) == 4 * (1024 * 27 * 1764 + 1024 * 16 + 2 * 1024 + 4)
     assert lib.ias_vicreg_workspace_bytes(8192, 256) > 2 * 2 * 8192 * 256 * 4
 
 
