@@ -74,6 +74,12 @@ IAS_API int ias_voice_sorted_index(int reg_index);
 IAS_API int ias_voice_seed_params(int64_t first_sound_id, int B, const uint8_t* frozen78_host, float* params01,
                           uint8_t* is_train, ias_stream_t stream);
 
+/* Same, with the batch number read from device memory when the kernel runs (first_sound_id = *batch_idx_dev * B):
+ * the step can be captured in a CUDA graph and replayed with a new batch number, and the host never has to read the
+ * DataLoader's integer back (the reference's `batch.cpu()` at vicreg_audio_params.py:109-112 is a synchronisation). */
+IAS_API int ias_voice_seed_params_dev(const int64_t* batch_idx_dev, int B, const uint8_t* frozen78_host, float* params01,
+                              uint8_t* is_train, ias_stream_t stream);
+
 IAS_API size_t ias_voice_workspace_bytes(int B, int T, int C);
 
 /* Control-rate stage only (keyboard, 6 ADSR, 2 LFO, modulation matrix): ctrl[B][5][C].  Inspection entry point
@@ -108,6 +114,17 @@ IAS_API int ias_pqmf_out_len(int T, int N, int K);
 IAS_API int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
                       const float* mod_host, const float* row_scale, float* out, int B, int T, int N, int K,
                       ias_stream_t stream);
+
+/* PQMF.analysis fused with the image preprocessing AudioEmbedding._preprocess applies to the bands
+ * (audioembed.py:38-49): z.reshape(-1,3,240,245) is a view of out[B][N][L]; img_preprocess is
+ * torchvision.transforms.Normalize(mean, std) (vicreg_audio_params.py:60-62), i.e. out[b][k][n] =
+ * (band[b][k][n] - mean[k]) / std[k] in fp32, applied in the store epilogue so the bands make one trip to HBM.
+ * mean_host[N], std_host[N] are host arrays; norm_dev = device [mean[N] | std[N]] is only read by the generic kernel
+ * (shapes without a specialised one) and may be NULL otherwise. */
+IAS_API int ias_pqmf_analysis_image(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
+                            const float* mod_host, const float* row_scale, const float* mean_host,
+                            const float* std_host, const float* norm_dev, float* out, int B, int T, int N, int K,
+                            ias_stream_t stream);
 
 /* PQMF.synthesis (pqmf.py:52-55): zero-stuff by N with gain N, then the N->1 FIR G = [N][K] (buffer G[0]).
  * y[b][t], t < L*N. */

@@ -32,6 +32,15 @@ struct TapsCM {
   float c[N * 2 * N];
 };
 
+// Optional per-band epilogue (band - mean[k]) / std[k]: torchvision.transforms.Normalize on the [B,3,240,245] image
+// view the reference takes of the bands (audioembed.py:41,49; constants vicreg_audio_params.py:60-62).
+template <int N>
+struct BandNorm {
+  float mean[N];
+  float std[N];
+  int on;
+};
+
 __host__ __device__ constexpr int odd_stride(int s) { return (s & 1) ? s : s + 1; }
 
 // Shared-memory layout of a staged signal row.  Thread t reads a sliding window that starts at linear index t*S, so
@@ -136,7 +145,7 @@ __device__ __forceinline__ void load_window(const float* __restrict__ src, float
 template <int N, int K, int Q, class TapsT>
 __global__ void __launch_bounds__(PQ_THREADS)
 k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale, float* __restrict__ out, int T, int L,
-                int tiles_per_row, TapsT taps) {
+                int tiles_per_row, TapsT taps, BandNorm<N> norm) {
   constexpr int PAD = (K - 1) / 2;
   constexpr int S = Q * N;                 // input samples consumed per thread
   constexpr int WIN = (Q - 1) * N + K;     // input window of one thread
@@ -202,6 +211,13 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
       for (int k = 0; k < N; ++k) acc[q][k] *= scale;
   }
 
+  if (norm.on) {  // tensor.sub_(mean).div_(std), fp32 ops as torch issues them
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int k = 0; k < N; ++k) acc[q][k] = __fdiv_rn(__fsub_rn(acc[q][k], norm.mean[k]), norm.std[k]);
+  }
+
   const int n0 = n_tile + threadIdx.x * Q;
   float* ob = out + (size_t)b * N * L;
   const bool st_vec = ((L & 3) == 0) && (Q % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
@@ -222,8 +238,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
 
 // Any (N, K): one thread per output, taps from global memory.  Correct for shapes without a specialised kernel.
 __global__ void k_pqmf_analysis_generic(const float* __restrict__ x, const float* __restrict__ H,
-                                        const float* __restrict__ row_scale, float* __restrict__ out, int B, int T,
-                                        int N, int K, int L) {
+                                        const float* __restrict__ row_scale, const float* __restrict__ norm_dev,
+                                        float* __restrict__ out, int B, int T, int N, int K, int L) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * N * L;
   if (idx >= total) return;
@@ -238,6 +254,7 @@ __global__ void k_pqmf_analysis_generic(const float* __restrict__ x, const float
     const int g = n * N + j - pad;
     if (g >= 0 && g < T) acc = fmaf(H[k * K + j], xr[g] * scale, acc);
   }
+  if (norm_dev) acc = __fdiv_rn(__fsub_rn(acc, norm_dev[k]), norm_dev[N + k]);  // [mean[N] | std[N]]
   out[idx] = acc;
 }
 
@@ -350,20 +367,27 @@ __global__ void k_pqmf_synthesis_generic(const float* __restrict__ z, const floa
 
 template <int N, int K, int Q>
 int launch_analysis(const float* x, const float* H_host, const float* proto_host, const float* mod_host,
-                    const float* row_scale, float* out, int B, int T, int L, cudaStream_t st) {
+                    const float* row_scale, const float* mean_host, const float* std_host, float* out, int B, int T,
+                    int L, cudaStream_t st) {
   constexpr int TILE_N = PQ_THREADS * Q;
   const int tiles = (L + TILE_N - 1) / TILE_N;
   const unsigned grid = (unsigned)((size_t)B * tiles);
+  BandNorm<N> norm;
+  norm.on = (mean_host && std_host) ? 1 : 0;
+  for (int k = 0; k < N; ++k) {
+    norm.mean[k] = norm.on ? mean_host[k] : 0.0f;
+    norm.std[k] = norm.on ? std_host[k] : 1.0f;
+  }
   ProfScope prof_(K_PQMF_ANALYSIS, st);
   if (proto_host && mod_host) {
     TapsCM<N, K> taps;
     for (int i = 0; i < K; ++i) taps.g[i] = proto_host[i];
     for (int i = 0; i < N * 2 * N; ++i) taps.c[i] = mod_host[i];
-    k_pqmf_analysis<N, K, Q, TapsCM<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps);
+    k_pqmf_analysis<N, K, Q, TapsCM<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm);
   } else {
     Taps<N, K> taps;
     for (int i = 0; i < N * K; ++i) taps.h[i] = H_host[i];
-    k_pqmf_analysis<N, K, Q, Taps<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps);
+    k_pqmf_analysis<N, K, Q, Taps<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm);
   }
   IAS_LAUNCH_CHECK("k_pqmf_analysis");
   return IAS_OK;
@@ -395,34 +419,59 @@ extern "C" int ias_pqmf_out_len(int T, int N, int K) {
   return span < 0 ? 0 : span / N + 1;
 }
 
-extern "C" int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
-                                 const float* mod_host, const float* row_scale, float* out, int B, int T, int N,
-                                 int K, ias_stream_t stream) {
-  IAS_REQUIRE(B > 0 && T > 0 && N > 0 && K > 0, IAS_ERR_INVALID, "ias_pqmf_analysis: B=%d T=%d N=%d K=%d", B, T, N, K);
-  IAS_REQUIRE(x && out, IAS_ERR_INVALID, "ias_pqmf_analysis: NULL pointer");
-  IAS_REQUIRE(H_dev || H_host, IAS_ERR_INVALID, "ias_pqmf_analysis: no filter given");
+namespace {
+int analysis_entry(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
+                   const float* mod_host, const float* row_scale, const float* mean_host, const float* std_host,
+                   const float* norm_dev, float* out, int B, int T, int N, int K, ias_stream_t stream, const char* who) {
+  IAS_REQUIRE(B > 0 && T > 0 && N > 0 && K > 0, IAS_ERR_INVALID, "%s: B=%d T=%d N=%d K=%d", who, B, T, N, K);
+  IAS_REQUIRE(x && out, IAS_ERR_INVALID, "%s: NULL pointer", who);
+  IAS_REQUIRE(H_dev || H_host, IAS_ERR_INVALID, "%s: no filter given", who);
   const int L = ias_pqmf_out_len(T, N, K);
-  IAS_REQUIRE(L > 0, IAS_ERR_INVALID, "ias_pqmf_analysis: empty output (T=%d K=%d)", T, K);
+  IAS_REQUIRE(L > 0, IAS_ERR_INVALID, "%s: empty output (T=%d K=%d)", who, T, K);
   cudaStream_t st = as_stream(stream);
   if (H_host && K == 63) {
+#define IAS_PQ(NN, QQ) \
+  case NN: return launch_analysis<NN, 63, QQ>(x, H_host, proto_host, mod_host, row_scale, mean_host, std_host, out, B, T, L, st);
     switch (N) {
-      case 2: return launch_analysis<2, 63, 8>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
-      case 3: return launch_analysis<3, 63, 8>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
-      case 4: return launch_analysis<4, 63, 8>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
-      case 8: return launch_analysis<8, 63, 4>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
-      case 16: return launch_analysis<16, 63, 2>(x, H_host, proto_host, mod_host, row_scale, out, B, T, L, st);
+      IAS_PQ(2, 8)
+      IAS_PQ(3, 8)
+      IAS_PQ(4, 8)
+      IAS_PQ(8, 4)
+      IAS_PQ(16, 2)
       default: break;
     }
+#undef IAS_PQ
   }
-  IAS_REQUIRE(H_dev, IAS_ERR_UNSUPPORTED, "ias_pqmf_analysis: N=%d K=%d has no specialised kernel and H_dev is NULL", N,
-              K);
+  IAS_REQUIRE(H_dev, IAS_ERR_UNSUPPORTED, "%s: N=%d K=%d has no specialised kernel and H_dev is NULL", who, N, K);
+  IAS_REQUIRE(!(mean_host && std_host) || norm_dev, IAS_ERR_UNSUPPORTED,
+              "%s: N=%d K=%d has no specialised kernel: the band normalisation needs norm_dev", who, N, K);
   const size_t total = (size_t)B * N * L;
   {
     ProfScope prof_(K_PQMF_ANALYSIS, st);
-    k_pqmf_analysis_generic<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, H_dev, row_scale, out, B, T, N, K, L);
+    k_pqmf_analysis_generic<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        x, H_dev, row_scale, (mean_host && std_host) ? norm_dev : nullptr, out, B, T, N, K, L);
   }
   IAS_LAUNCH_CHECK("k_pqmf_analysis_generic");
   return IAS_OK;
+}
+}  // namespace
+
+extern "C" int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
+                                 const float* mod_host, const float* row_scale, float* out, int B, int T, int N,
+                                 int K, ias_stream_t stream) {
+  return analysis_entry(x, H_dev, H_host, proto_host, mod_host, row_scale, nullptr, nullptr, nullptr, out, B, T, N, K,
+                        stream, "ias_pqmf_analysis");
+}
+
+extern "C" int ias_pqmf_analysis_image(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
+                                       const float* mod_host, const float* row_scale, const float* mean_host,
+                                       const float* std_host, const float* norm_dev, float* out, int B, int T, int N,
+                                       int K, ias_stream_t stream) {
+  IAS_REQUIRE(mean_host && std_host, IAS_ERR_INVALID, "ias_pqmf_analysis_image: mean/std missing");
+  for (int k = 0; k < N; ++k)
+    IAS_REQUIRE(std_host[k] != 0.0f, IAS_ERR_INVALID, "ias_pqmf_analysis_image: std[%d] == 0", k);
+  return analysis_entry(x, H_dev, H_host, proto_host, mod_host, row_scale, mean_host, std_host, norm_dev, out, B, T, N,
+                        K, stream, "ias_pqmf_analysis_image");
 }
 
 extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, float* y, int B, int L,

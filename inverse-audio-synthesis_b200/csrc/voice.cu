@@ -73,10 +73,12 @@ struct SeedTable {
   uint8_t frozen[NROWS];
 };
 
-__global__ void __launch_bounds__(128) k_seed_params(long long first_id, int B, SeedTable tab,
-                                                     float* __restrict__ params01, uint8_t* __restrict__ is_train) {
+__global__ void __launch_bounds__(128) k_seed_params(long long first_id, const long long* __restrict__ batch_idx_dev,
+                                                     int B, SeedTable tab, float* __restrict__ params01,
+                                                     uint8_t* __restrict__ is_train) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
+  if (batch_idx_dev) first_id = *batch_idx_dev * (long long)B;  // batch number read on the device (graph replay)
   unsigned long long id = (unsigned long long)(first_id + i);
   // MT19937 state after init_genrand(low 32 bits of the seed); only mt[0..78] and mt[397..474] feed outputs 0..77
   uint32_t lo[NROWS + 1];
@@ -140,7 +142,11 @@ struct ControlShared {
 //   [6..8]  AmpLine of vco_1_amp  * mixer level 1
 //   [9..11] AmpLine of vco_2_amp  * mixer level 2 * (1 - shape/2)
 //   [12..14] AmpLine of noise_amp * mixer level 3
-__global__ void __launch_bounds__(CTRL_THREADS)
+// Measured (r01j, 1024 voices): pow out of line + 2 CTAs/SM 0.191 ms; inlined 0.219; 3 CTAs/SM spills: 0.224-0.259.
+#ifndef IAS_CTRL_MINB
+#define IAS_CTRL_MINB 2
+#endif
+__global__ void __launch_bounds__(CTRL_THREADS, IAS_CTRL_MINB)
 k_voice_control(const float* __restrict__ params01, int B, int C, float cr, float eps, RangeTable ranges,
                 const float* __restrict__ ctrl_in, float* __restrict__ ctrl, float* __restrict__ scratch,
                 float* __restrict__ vconst, float4* __restrict__ rec) {
@@ -151,26 +157,28 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
 
   if (tid < NROWS) sh.P[tid] = from_0to1(params01[(size_t)tid * B + b], ranges.r[tid]);
   __syncthreads();
-  if (tid < 6) {
+  // per-voice setup, one item per thread of four different warps so the serial pow / division chains overlap
+  if (tid < 18) {  // 6 envelopes x {attack, decay, release}
     const int base[6] = {ADSR1, ADSR2, LFO1_AMP, LFO2_AMP, LFO1_RATE, LFO2_RATE};
-    sh.adsr[tid] = adsr_setup(&sh.P[base[tid]], sh.P[KEY_DURATION], cr, eps);
-  } else if (tid < 8) {
-    sh.lfo[tid - 6] = lfo_setup(&sh.P[tid == 6 ? LFO1 : LFO2]);
-  } else if (tid == 8) {
+    adsr_setup_part(sh.adsr[tid / 3], tid % 3, &sh.P[base[tid / 3]], sh.P[KEY_DURATION], cr, eps, C);
+  } else if (tid >= 32 && tid < 34) {
+    sh.lfo[tid - 32] = lfo_setup(&sh.P[tid == 32 ? LFO1 : LFO2]);
+  } else if (tid == 64) {
     sh.mm = modmatrix_setup(&sh.P[MODM]);
-  } else if (tid == 9) {
+  } else if (tid == 96) {
     voice_constants(sh.P, vconst + (size_t)b * VC_COUNT);
   }
   __syncthreads();
 
   float* sc = scratch + (size_t)b * 6 * C;  // [6][C]: x1|arg1, x2|arg2, amp1, amp2, adsr_1, adsr_2
   // Phase A: pointwise envelopes and LFO phase increments
+  const float rcr = rcp(cr);
   for (int j = tid; j < C; j += CTRL_THREADS) {
     float n = (float)j;
     float rate1 = adsr_eval(sh.adsr[4], n, eps);
     float rate2 = adsr_eval(sh.adsr[5], n, eps);
-    sc[0 * C + j] = lfo_increment(sh.lfo[0], rate1, cr);
-    sc[1 * C + j] = lfo_increment(sh.lfo[1], rate2, cr);
+    sc[0 * C + j] = lfo_increment(sh.lfo[0], rate1, cr, rcr);
+    sc[1 * C + j] = lfo_increment(sh.lfo[1], rate2, cr, rcr);
     sc[2 * C + j] = adsr_eval(sh.adsr[2], n, eps);
     sc[3 * C + j] = adsr_eval(sh.adsr[3], n, eps);
     sc[4 * C + j] = adsr_eval(sh.adsr[0], n, eps);
@@ -310,6 +318,10 @@ k_voice_schedule(const float* __restrict__ vconst, int B, int T, float scale, in
 // ------------------------------------------------------------------------------------------------------------
 // k_voice_audio
 // ------------------------------------------------------------------------------------------------------------
+#ifndef IAS_AUDIO_PREFETCH
+#define IAS_AUDIO_PREFETCH 1
+#endif
+
 struct AudioArgs {
   const float4* rec;    // [B][C][4] per-interval records (k_voice_control)
   const float* vconst;  // [B][16]
@@ -326,12 +338,15 @@ struct AudioArgs {
   int normalize;
 };
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // Persistent CTAs pull voices from the queue.  Per voice: tiles of NT*SPT samples, SPT consecutive samples per thread.
 //   pass 1  pitch path of both VCOs, bit for bit the reference's fp32 op sequence -> phase increments x1, x2
 //   scan    fp64 block scan of the increments (exact for 4 s clips), carry across tiles
 //   pass 2  oscillators, VCA gains (AmpLine), noise, mix, running peak
 template <int NT, int SPT, int MINB, bool VEC, bool DBG>
 __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
+  constexpr bool PREFETCH = IAS_AUDIO_PREFETCH != 0;
   constexpr int TILE = NT * SPT;
   constexpr int NW = NT / 32;
   __shared__ double s_wsum[2][2][NW];  // [buffer][vco][warp]
@@ -367,6 +382,13 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
       const float fj = (float)j;
       const float fj1 = add(fj, 1.0f);
       const float4* rj = rec + (size_t)j * 4;
+      if (PREFETCH && tile + 1 < ntiles) {
+        // the next tile's record (64 B) and noise (4*SPT B) of this thread: bring them into L1 now, so the loads at
+        // the top of the next iteration do not expose an L2 / HBM round trip (they were ~10 % of the stall samples)
+        const int jn = min((int)mul(scale, fminf(add(ft0, (float)TILE), (float)(T - 1))), C - 1);
+        prefetch_l1(rec + (size_t)jn * 4);
+        if (VEC && t0 + TILE < T) prefetch_l1(nz + t0 + TILE);
+      }
       // ---- pass 1: phase increments of both VCOs ---------------------------------------------------------
       float x1[SPT], x2[SPT], srcs[SPT];
       const float4 r0 = __ldg(rj + 0);
@@ -617,6 +639,9 @@ int launch_audio(const AudioArgs& a, const VoiceWorkspace& w, bool dbg, cudaStre
   IAS_SHAPE(128, 16, 3)
   IAS_SHAPE(256, 8, 3)
   IAS_SHAPE(256, 16, 2)
+  IAS_SHAPE(128, 12, 5)
+  IAS_SHAPE(96, 16, 5)
+  IAS_SHAPE(64, 16, 8)
   return set_err(IAS_ERR_UNSUPPORTED, "ias_voice_render: no audio kernel of shape %dx%dx%d", s.nt, s.spt, s.ctas_per_sm);
 #undef IAS_SHAPE
   IAS_LAUNCH_CHECK("k_voice_audio");
@@ -638,10 +663,11 @@ extern "C" int ias_voice_sorted_index(int reg_index) {
   return names().sorted_index[reg_index];
 }
 
-extern "C" int ias_voice_seed_params(int64_t first_sound_id, int B, const uint8_t* frozen78_host, float* params01,
-                                     uint8_t* is_train, ias_stream_t stream) {
-  IAS_REQUIRE(B > 0, IAS_ERR_INVALID, "ias_voice_seed_params: B=%d", B);
-  IAS_REQUIRE(params01 != nullptr, IAS_ERR_INVALID, "ias_voice_seed_params: params01 is NULL");
+namespace {
+int seed_params(int64_t first_sound_id, const int64_t* batch_idx_dev, int B, const uint8_t* frozen78_host,
+                float* params01, uint8_t* is_train, ias_stream_t stream, const char* who) {
+  IAS_REQUIRE(B > 0, IAS_ERR_INVALID, "%s: B=%d", who, B);
+  IAS_REQUIRE(params01 != nullptr, IAS_ERR_INVALID, "%s: params01 is NULL", who);
   SeedTable tab;
   for (int i = 0; i < vm::NROWS; ++i) {
     tab.reg_of_sorted[i] = names().reg_of_sorted[i];
@@ -649,11 +675,23 @@ extern "C" int ias_voice_seed_params(int64_t first_sound_id, int B, const uint8_
   }
   {
     ProfScope prof_(K_SEED_PARAMS, as_stream(stream));
-    k_seed_params<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>((long long)first_sound_id, B, tab, params01,
-                                                                  is_train);
+    k_seed_params<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(
+        (long long)first_sound_id, reinterpret_cast<const long long*>(batch_idx_dev), B, tab, params01, is_train);
   }
   IAS_LAUNCH_CHECK("k_seed_params");
   return IAS_OK;
+}
+}  // namespace
+
+extern "C" int ias_voice_seed_params(int64_t first_sound_id, int B, const uint8_t* frozen78_host, float* params01,
+                                     uint8_t* is_train, ias_stream_t stream) {
+  return seed_params(first_sound_id, nullptr, B, frozen78_host, params01, is_train, stream, "ias_voice_seed_params");
+}
+
+extern "C" int ias_voice_seed_params_dev(const int64_t* batch_idx_dev, int B, const uint8_t* frozen78_host,
+                                         float* params01, uint8_t* is_train, ias_stream_t stream) {
+  IAS_REQUIRE(batch_idx_dev != nullptr, IAS_ERR_INVALID, "ias_voice_seed_params_dev: batch_idx_dev is NULL");
+  return seed_params(0, batch_idx_dev, B, frozen78_host, params01, is_train, stream, "ias_voice_seed_params_dev");
 }
 
 extern "C" size_t ias_voice_workspace_bytes(int B, int T, int C) {

@@ -77,6 +77,24 @@ IAS_HD float div_const(float a, float c, float rc) {
   return fma(r, rc, q);
 }
 
+// 1 / x, correctly rounded (== div(1.0f, x))
+IAS_HD float rcp(float x) {
+#ifdef __CUDA_ARCH__
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+
+// a / c for a divisor that is constant per voice, rc = rcp(c): two Markstein correction steps.  The first makes the
+// quotient faithful for any normal c, the second rounds it correctly (tests/test_voice_math.py checks it against IEEE
+// division over the ranges the ADSR ramps use).  Requires c, rc and the quotient to be normal numbers.
+IAS_HD float div_pre(float a, float c, float rc) {
+  float q = mul(a, rc);
+  q = fma(fma(-q, c, a), rc, q);
+  return fma(fma(-q, c, a), rc, q);
+}
+
 #define IAS_PI_F 3.14159274101257324f       /* (float)math.pi       */
 #define IAS_TWO_PI_F 6.28318548202514648f   /* (float)(2 * math.pi) */
 
@@ -161,7 +179,7 @@ IAS_HD F2 df_squ(F2 x) {
   return f2(s, fma(add(x.x, x.x), x.y, fma(x.x, x.x, -s)));
 }
 IAS_HD F2 df_div(F2 n, F2 d) {
-  float t = div(1.0f, d.x);
+  float t = rcp(d.x);
   float s = mul(n.x, t);
   float u = fma(t, n.x, -s);
   float v = fma(-d.y, t, fma(-d.x, t, 1.0f));
@@ -210,10 +228,20 @@ IAS_HD float sleef_expk(F2 d) {
   return u;
 }
 
+// One out-of-line copy on the device: the control kernel calls it from 18 ramps + 10 LFO weights, and 28 inlined
+// copies (~300 instructions each) do not fit the instruction cache.
+#if defined(__CUDACC__) && defined(IAS_POW_NOINLINE)
+__host__ __device__ __noinline__ float pow_sleef_core(float r, float a) {
+#else
+IAS_HD float pow_sleef_core(float r, float a) {
+#endif
+  return sleef_expk(df_mul_f2_f(sleef_logk(r), a));
+}
+
 IAS_HD float pow_sleef(float r, float a) {  // r >= 0, a > 0 (ADSR ramps, LFO mode weights)
   if (r == 1.0f) return 1.0f;
   if (r == 0.0f) return 0.0f;
-  return sleef_expk(df_mul_f2_f(sleef_logk(r), a));
+  return pow_sleef_core(r, a);
 }
 
 // ---- correctly rounded (double evaluation, one final rounding) stand-ins for the SLEEF functions that are not
@@ -289,49 +317,93 @@ inline RangeTable make_range_table() {
 }
 
 // ---- ADSR (torchsynth module.py ADSR; oracle/voice.py _adsr) -------------------------------------------------
-struct Adsr {
-  float a_dur, d_dur, d_start, r_dur, r_start;  // control-rate samples
-  float sustain, one_minus_sustain, alpha;
-  float d_pre, r_pre;  // value of the decay / release ramp at every n <= its start (max(n - start, 0) == 0 there)
+// One ramp of the envelope: r(n) = min((max(n - start, 0) + eps) / dur + eps, 1), inverted to 1 - r when `inverse` and
+// dur > 0, then raised to alpha.  r is non-decreasing in n, so it is constant before `start` and exactly 1 from some
+// integer n on; both thresholds are found per voice (with the very same fp32 expression) so that the per-point
+// evaluation skips the division and the pow outside the ramp's active span.
+struct Ramp {
+  float dur, rdur, start;
+  float sat_from;  // first integer n (as float) with r(n) == 1; >= 1e30 if none was found below the search limit
+  float pre, post; // value of the finished ramp (after inversion and pow) for n <= start / n >= sat_from
+  int fast_div;    // dur normal and well inside the exponent range: division through rdur = rcp(dur)
+  int inverse;
 };
 
-IAS_HD float adsr_ramp(float n, float dur, float start, bool inverse, float alpha, float eps) {
-  float r = fmaxf(sub(n, start), 0.0f);
-  r = add(div(add(r, eps), dur), eps);
-  r = fminf(r, 1.0f);
-  if (inverse && dur > 0.0f) r = sub(1.0f, r);
+IAS_HD float ramp_raw(const Ramp& p, float n, float eps) {
+  float r = fmaxf(sub(n, p.start), 0.0f);
+  r = add(r, eps);
+  r = p.fast_div ? div_pre(r, p.dur, p.rdur) : div(r, p.dur);
+  return fminf(add(r, eps), 1.0f);
+}
+
+IAS_HD float ramp_finish(const Ramp& p, float r, float alpha) {
+  if (p.inverse && p.dur > 0.0f) r = sub(1.0f, r);
   return pow_sleef(r, alpha);
 }
 
-// Call after the other fields are set: the inverse ramps are constant up to their start sample, so that value
-// (the same expression evaluated once) replaces a pow per control point there.
-IAS_HD void adsr_precompute(Adsr& p, float eps) {
-  p.d_pre = adsr_ramp(0.0f, p.d_dur, 0.0f, true, p.alpha, eps);
-  p.r_pre = adsr_ramp(0.0f, p.r_dur, 0.0f, true, p.alpha, eps);
+IAS_HD Ramp ramp_setup(float dur, float start, bool inverse, float alpha, float eps, int n_limit) {
+  Ramp p;
+  p.dur = dur;
+  p.start = start;
+  p.inverse = inverse ? 1 : 0;
+  p.fast_div = (dur > 1e-20f && dur < 1e20f) ? 1 : 0;
+  p.rdur = p.fast_div ? rcp(dur) : 0.0f;
+  const float r0 = ramp_raw(p, 0.0f < start ? 0.0f : start, eps);  // max(n - start, 0) == 0 for every n <= start
+  p.pre = ramp_finish(p, r0, alpha);
+  p.post = ramp_finish(p, 1.0f, alpha);
+  if (r0 == 1.0f) {  // zero (or tiny) duration: saturated everywhere
+    p.sat_from = 0.0f;
+    return p;
+  }
+  // first integer n with r(n) == 1: it lies above `start`; begin at the real-valued estimate and walk (r is monotone)
+  float est = ceilf(add(start, dur));
+  int n0 = est < 0.0f ? 0 : (est > (float)n_limit ? n_limit : (int)est);
+  while (n0 > 0 && (float)(n0 - 1) > start && ramp_raw(p, (float)(n0 - 1), eps) == 1.0f) --n0;
+  while (n0 < n_limit && ramp_raw(p, (float)n0, eps) != 1.0f) ++n0;
+  p.sat_from = n0 < n_limit ? (float)n0 : 1e30f;
+  return p;
 }
 
-// v[] = {attack, decay, sustain, release, alpha} already through from_0to1.
-IAS_HD Adsr adsr_setup(const float* v, float note_on, float cr, float eps) {
+IAS_HD float ramp_eval(const Ramp& p, float n, float alpha, float eps) {
+  if (n >= p.sat_from) return p.post;
+  if (n <= p.start) return p.pre;
+  return ramp_finish(p, ramp_raw(p, n, eps), alpha);
+}
+
+struct Adsr {
+  Ramp a, d, r;
+  float sustain, one_minus_sustain, alpha;
+};
+
+// v[] = {attack, decay, sustain, release, alpha} already through from_0to1; n_limit = number of control points.
+// `which` selects the part to fill (0 attack + scalars, 1 decay, 2 release) so three threads can share one envelope.
+IAS_HD void adsr_setup_part(Adsr& p, int which, const float* v, float note_on, float cr, float eps, int n_limit) {
+  const float new_attack = fminf(v[0], note_on);
+  const float alpha = v[4];
+  if (which == 0) {
+    p.sustain = v[2];
+    p.one_minus_sustain = sub(1.0f, v[2]);
+    p.alpha = alpha;
+    p.a = ramp_setup(mul(new_attack, cr), 0.0f, false, alpha, eps, n_limit);
+  } else if (which == 1) {
+    const float new_decay = fminf(fmaxf(sub(note_on, v[0]), 0.0f), v[1]);
+    p.d = ramp_setup(mul(new_decay, cr), mul(new_attack, cr), true, alpha, eps, n_limit);
+  } else {
+    p.r = ramp_setup(mul(v[3], cr), mul(note_on, cr), true, alpha, eps, n_limit);
+  }
+}
+
+IAS_HD Adsr adsr_setup(const float* v, float note_on, float cr, float eps, int n_limit) {
   Adsr p;
-  float new_attack = fminf(v[0], note_on);
-  float new_decay = fminf(fmaxf(sub(note_on, v[0]), 0.0f), v[1]);
-  p.a_dur = mul(new_attack, cr);
-  p.d_dur = mul(new_decay, cr);
-  p.d_start = mul(new_attack, cr);
-  p.r_dur = mul(v[3], cr);
-  p.r_start = mul(note_on, cr);
-  p.sustain = v[2];
-  p.one_minus_sustain = sub(1.0f, v[2]);
-  p.alpha = v[4];
-  adsr_precompute(p, eps);
+  for (int which = 0; which < 3; ++which) adsr_setup_part(p, which, v, note_on, cr, eps, n_limit);
   return p;
 }
 
 IAS_HD float adsr_eval(const Adsr& p, float n, float eps) {
-  float a = adsr_ramp(n, p.a_dur, 0.0f, false, p.alpha, eps);
-  float d = n <= p.d_start ? p.d_pre : adsr_ramp(n, p.d_dur, p.d_start, true, p.alpha, eps);
+  float a = ramp_eval(p.a, n, p.alpha, eps);
+  float d = ramp_eval(p.d, n, p.alpha, eps);
   float dk = add(mul(p.one_minus_sustain, d), p.sustain);
-  float r = n <= p.r_start ? p.r_pre : adsr_ramp(n, p.r_dur, p.r_start, true, p.alpha, eps);
+  float r = ramp_eval(p.r, n, p.alpha, eps);
   return mul(mul(a, dk), r);
 }
 
@@ -360,6 +432,11 @@ IAS_HD float lfo_increment(const Lfo& l, float mod, float cr) {
   float f = fmaxf(add(l.frequency, mul(l.mod_depth, mod)), 0.0f);
   return div(mul(IAS_TWO_PI_F, f), cr);
 }
+// same with rcr = rcp(cr) hoisted by the caller (cr is a launch constant)
+IAS_HD float lfo_increment(const Lfo& l, float mod, float cr, float rcr) {
+  float f = fmaxf(add(l.frequency, mul(l.mod_depth, mod)), 0.0f);
+  return div_pre(mul(IAS_TWO_PI_F, f), cr, rcr);
+}
 
 IAS_HD float lfo_shapes_mix(const Lfo& l, float arg) {
   float c = cos_cr(add(arg, IAS_PI_F));
@@ -368,7 +445,7 @@ IAS_HD float lfo_shapes_mix(const Lfo& l, float arg) {
   sq = mul(add(sq, 1.0f), 0.5f);
   float m = fmodf(arg, IAS_TWO_PI_F);
   if (m != 0.0f && m < 0.0f) m = add(m, IAS_TWO_PI_F);
-  float saw = div(m, IAS_TWO_PI_F);
+  float saw = div_const(m, IAS_TWO_PI_F, 0.159154936671257019f);  // RN(1 / (float)(2 pi))
   float rsaw = sub(1.0f, saw);
   float tri = mul(2.0f, saw);
   if (tri > 1.0f) tri = sub(2.0f, tri);

@@ -12,7 +12,7 @@ import subprocess
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libias_b200.so")
+LIB_PATH = os.environ.get("IAS_B200_LIB") or os.path.join(_HERE, "libias_b200.so")  # override: tuning builds only
 COMM_LIB_PATH = os.path.join(_HERE, "libias_comm.so")
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
@@ -52,6 +52,7 @@ _SIGNATURES = {
     "ias_voice_param_name": (c_char_p, [c_int]),
     "ias_voice_sorted_index": (c_int, [c_int]),
     "ias_voice_seed_params": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ias_voice_seed_params_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ias_voice_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ias_voice_control": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ias_voice_render": (
@@ -62,6 +63,8 @@ _SIGNATURES = {
     "ias_pqmf_out_len": (c_int, [c_int, c_int, c_int]),
     "ias_pqmf_analysis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_int, c_void_p]),
+    "ias_pqmf_analysis_image": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ias_pqmf_synthesis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ias_vicreg_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ias_vicreg_loss": (

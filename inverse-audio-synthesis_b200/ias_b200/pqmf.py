@@ -83,7 +83,25 @@ class PQMF(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.analysis(x)
 
-    def analysis(self, x: torch.Tensor, row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def analysis_image(self, x: torch.Tensor, mean, std, image_shape: Optional[Tuple[int, int]] = None,
+                       row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``AudioEmbedding._preprocess`` in one kernel (audioembed.py:36-49): bands -> ``reshape(-1, N, H, W)`` ->
+        ``torchvision.transforms.Normalize(mean, std)``.  ``mean`` / ``std`` are length-N sequences (the reference:
+        ImageNet constants, vicreg_audio_params.py:60-62).  Returns ``[B, N, H, W]`` when ``image_shape=(H, W)`` is given
+        (H*W must equal L; the reference uses (240, 245) for 4 s), else ``[B, N, L]``."""
+        mean_t = torch.as_tensor(mean, dtype=torch.float32).reshape(-1).contiguous().cpu()
+        std_t = torch.as_tensor(std, dtype=torch.float32).reshape(-1).contiguous().cpu()
+        if mean_t.numel() != self.N or std_t.numel() != self.N:
+            raise ValueError(f"analysis_image: mean/std need {self.N} entries")
+        out = self.analysis(x, row_scale=row_scale, _norm=(mean_t, std_t))
+        if image_shape is not None:
+            h, w = image_shape
+            if h * w != out.shape[2]:
+                raise ValueError(f"analysis_image: {h}x{w} != L={out.shape[2]}")
+            out = out.reshape(-1, self.N, h, w)
+        return out
+
+    def analysis(self, x: torch.Tensor, row_scale: Optional[torch.Tensor] = None, _norm=None) -> torch.Tensor:
         """x [B,1,T] -> [B,N,L]  (pqmf.py:49-50).  ``row_scale`` [B] optionally scales each row on the fly."""
         if x.dim() != 3 or x.shape[1] != 1:
             raise ValueError(f"PQMF.analysis expects [B,1,T], got {tuple(x.shape)}")
@@ -102,6 +120,14 @@ class PQMF(nn.Module):
         out = torch.empty((B, self.N, L), dtype=torch.float32, device=x.device)
         if row_scale is not None:
             row_scale = row_scale.detach().to(torch.float32).contiguous()
+        if _norm is not None:
+            mean_t, std_t = _norm
+            norm_dev = torch.cat([mean_t, std_t]).to(x.device)
+            rc = lib.ias_pqmf_analysis_image(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto), _lib.ptr(mod),
+                                             _lib.ptr(row_scale), _lib.ptr(mean_t), _lib.ptr(std_t), _lib.ptr(norm_dev),
+                                             _lib.ptr(out), B, T, self.N, K, _lib.current_stream(x.device))
+            _lib.check(rc, "ias_pqmf_analysis_image")
+            return out
         rc = lib.ias_pqmf_analysis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto), _lib.ptr(mod),
                                    _lib.ptr(row_scale), _lib.ptr(out), B, T, self.N, K,
                                    _lib.current_stream(x.device))

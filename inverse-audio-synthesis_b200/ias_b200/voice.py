@@ -371,6 +371,15 @@ class Voice(nn.Module):
             return
         _lib.require_cuda(self._store, "Voice parameters")
         frozen = (_lib.c_uint8 * _lib.NPARAMS)(*self._frozen_rows())
+        if isinstance(seed, torch.Tensor) and seed.is_cuda:
+            # the batch number stays on the device: no host read-back, and the call can be captured in a CUDA graph
+            if seed.dtype != torch.int64 or seed.numel() != 1:
+                raise ValueError("a device-resident batch index must be a single int64")
+            rc = _lib.lib().ias_voice_seed_params_dev(
+                _lib.ptr(seed), self.batch_size, frozen, _lib.ptr(self._store), _lib.ptr(self._is_train),
+                _lib.current_stream(self.device))
+            _lib.check(rc, "ias_voice_seed_params_dev")
+            return
         rc = _lib.lib().ias_voice_seed_params(
             int(seed) * self.batch_size, self.batch_size, frozen, _lib.ptr(self._store), _lib.ptr(self._is_train),
             _lib.current_stream(self.device))
@@ -421,14 +430,17 @@ class Voice(nn.Module):
         self._tie()
         return self._store.t().contiguous()
 
-    def forward(self, batch_idx: Optional[int] = None):
-        """-> (audio[B,T], params[B,78], is_train[B] or None)  (vicreg_audio_params.py:114)."""
+    def forward(self, batch_idx=None):
+        """-> (audio[B,T], params[B,78], is_train[B] or None)  (vicreg_audio_params.py:114).  ``batch_idx`` is an int
+        (or anything ``int()`` accepts, as in the reference) or a one-element int64 CUDA tensor, which is read on the
+        device."""
         if self.synthconfig.reproducible and batch_idx is None:
             raise ValueError("Reproducible mode is on, you must pass a batch index")
         ctx = torch.no_grad() if self.synthconfig.no_grad else torch.enable_grad()
         with ctx:
             if batch_idx is not None:
-                self.randomize(seed=int(batch_idx))  # ties the parameter views
+                on_device = isinstance(batch_idx, torch.Tensor) and batch_idx.is_cuda
+                self.randomize(seed=batch_idx if on_device else int(batch_idx))  # ties the parameter views
                 is_train = self._is_train.bool()
             else:
                 self._tie()

@@ -16,6 +16,10 @@ void shim_div_const(const float* x, float c, float* y, long n) {
   float rc = 1.0f / c;
   for (long i = 0; i < n; ++i) y[i] = div_const(x[i], c, rc);
 }
+// a[i] / c[i] through the per-voice-constant path (rcp + two Markstein steps)
+void shim_div_pre(const float* a, const float* c, float* y, long n) {
+  for (long i = 0; i < n; ++i) y[i] = div_pre(a[i], c[i], rcp(c[i]));
+}
 void shim_sincos_arg(const float* x, float* s, float* c, long n) { for (long i = 0; i < n; ++i) sincos_arg(x[i], s[i], c[i]); }
 void shim_cos_arg(const float* x, float* c, long n) { for (long i = 0; i < n; ++i) c[i] = cos_arg(x[i]); }
 
@@ -34,7 +38,7 @@ void shim_control(const float* params01, int B, int C, float cr, float eps, floa
     for (int r = 0; r < NROWS; ++r) P[r] = from_0to1(params01[(size_t)r * B + b], t.r[r]);
     const int base[6] = {ADSR1, ADSR2, LFO1_AMP, LFO2_AMP, LFO1_RATE, LFO2_RATE};
     Adsr ad[6];
-    for (int i = 0; i < 6; ++i) ad[i] = adsr_setup(&P[base[i]], P[KEY_DURATION], cr, eps);
+    for (int i = 0; i < 6; ++i) ad[i] = adsr_setup(&P[base[i]], P[KEY_DURATION], cr, eps, C);
     Lfo lf[2] = {lfo_setup(&P[LFO1]), lfo_setup(&P[LFO2])};
     ModMatrix mm = modmatrix_setup(&P[MODM]);
     voice_constants(P, vconst + (size_t)b * VC_COUNT);
@@ -45,7 +49,7 @@ void shim_control(const float* params01, int B, int C, float cr, float eps, floa
       for (int i = 0; i < 6; ++i) e[i] = adsr_eval(ad[i], n, eps);
       float l[2];
       for (int k = 0; k < 2; ++k) {
-        acc[k] += (double)lfo_increment(lf[k], e[4 + k], cr);
+        acc[k] += (double)lfo_increment(lf[k], e[4 + k], cr, rcp(cr));
         float arg = add((float)acc[k], lf[k].initial_phase);
         l[k] = mul(lfo_shapes_mix(lf[k], arg), e[2 + k]);
       }

@@ -70,3 +70,49 @@ def test_bridge_pool_kernel_matches_torch(cuda_device):
         finally:
             harness.EMBED_DIM = harness_dim
         assert float((x.cpu().double() - ref).abs().max() / ref.abs().max()) <= 1e-6
+
+
+def test_device_batch_index_and_cuda_graph_replay(cuda_device):
+    """Voice(batch_idx) with the batch number resident on the device (ias_voice_seed_params_dev): same result as the
+    host integer, and the whole step replays from a CUDA graph with a new batch number each time."""
+    import ias_b200
+
+    B = 32
+    cfg = ias_b200.SynthConfig(batch_size=B, reproducible=True, sample_rate=44100, buffer_size_seconds=1.0)
+    voice = ias_b200.Voice(synthconfig=cfg).to(cuda_device)
+    gram = ias_b200.PQMF(N=3).to(cuda_device)
+    vcfg = types.SimpleNamespace(dim=256, embeddim=256, vicreg=types.SimpleNamespace(
+        mlp="8-8-%d", batch_size=B, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
+    vic = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity())
+    wa, wp = harness.bridge_weights(cuda_device)
+
+    def step(idx):
+        audio, params, is_train = voice(idx)
+        bands = gram(audio.unsqueeze(1))
+        x, y = harness.bridge(bands, params, wa, wp)
+        with torch.no_grad():
+            return audio, params, is_train, torch.stack(vic.loss(x, y))
+
+    want = {i: [t.clone() for t in step(i)] for i in (3, 11, 2 ** 33 + 5)}
+    idx_dev = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    for i, w in want.items():  # eager, device-resident index
+        idx_dev.fill_(i)
+        got = step(idx_dev)
+        for a, b in zip(got, w):
+            assert torch.equal(a, b)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(idx_dev)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static = step(idx_dev)
+    host_idx = torch.zeros(1, dtype=torch.int64).pin_memory()
+    for i, w in want.items():
+        host_idx[0] = i
+        idx_dev.copy_(host_idx, non_blocking=True)
+        graph.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(static, w):
+            assert torch.equal(a, b)

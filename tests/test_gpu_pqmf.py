@@ -156,3 +156,26 @@ def test_checkpoint_loaded_filter_is_used(cuda_device):
     sd["H"] = sd["H"] * 2.0
     m.load_state_dict(sd)
     assert float((m(x) - 2 * z0).abs().max()) <= 1e-6 * float(z0.abs().max())
+
+
+def test_image_epilogue_matches_reshape_plus_normalize(cuda_device):
+    """AudioEmbedding._preprocess (audioembed.py:36-49): gram(audio).reshape(-1,3,240,245) then Normalize(mean, std)
+    (vicreg_audio_params.py:60-62).  The fused epilogue applies torch's own fp32 sub/div, so it is bit-identical to
+    running them on the unfused bands."""
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    m = _mod(3, 0.15, cuda_device)
+    x = MG.pqmf_input(4, 176400).to(cuda_device)
+    z = m(x).reshape(-1, 3, 240, 245)
+    want = (z - torch.tensor(mean, device=cuda_device).view(1, 3, 1, 1)) / torch.tensor(std, device=cuda_device).view(1, 3, 1, 1)
+    got = m.analysis_image(x, mean, std, image_shape=(240, 245))
+    assert got.shape == (4, 3, 240, 245)
+    assert torch.equal(got, want)
+    # a shape without a specialised kernel (N=5) goes through the generic kernel's epilogue
+    m5 = _mod(5, 0.1, cuda_device)
+    x5 = MG.pqmf_input(2, 5000).to(cuda_device)
+    mean5, std5 = [0.1, -0.2, 0.3, 0.0, 1.5], [0.5, 2.0, 0.25, 1.0, 3.0]
+    z5 = m5(x5)
+    want5 = (z5 - torch.tensor(mean5, device=cuda_device).view(1, 5, 1)) / torch.tensor(std5, device=cuda_device).view(1, 5, 1)
+    assert torch.equal(m5.analysis_image(x5, mean5, std5), want5)
+    with pytest.raises(ValueError):
+        m.analysis_image(x, mean[:2], std[:2])

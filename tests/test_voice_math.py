@@ -50,6 +50,25 @@ def test_constant_division_is_ieee(voice_shim):
     assert _neq(y, x / 48000.0) == 0
 
 
+def test_division_by_per_voice_constant_is_ieee(voice_shim):
+    """ADSR ramps divide by a duration that is constant per voice: rcp + two Markstein steps == IEEE division."""
+    g = torch.Generator().manual_seed(8)
+    n = 8_000_000
+    a = (torch.rand(n, generator=g) * 14000).float() + 1e-6          # max(n - start, 0) + eps, up to 30 s of control points
+    c = torch.exp(torch.rand(n, generator=g) * 30 - 14).float()       # durations 1e-6 .. 1e7 control samples
+    c[:4] = torch.tensor([882.0, 2205.0, 1.9999999, 0.99999994])      # all-ones mantissas included
+    a[n // 2:] = torch.randint(0, 13230, (n - n // 2,), generator=g).float() + 1e-6
+    y = torch.empty_like(a)
+    voice_shim.shim_div_pre(P(a), P(c), P(y), ctypes.c_long(n))
+    assert _neq(y, a / c) == 0
+    x = (torch.rand(n, generator=g) * 6.2831855).float()
+    voice_shim.shim_div_const(P(x), F(6.2831854820251465), P(y), ctypes.c_long(n))
+    assert _neq(y, x / 6.2831854820251465) == 0
+    x = (torch.rand(n, generator=g) * 900).float()
+    voice_shim.shim_div_pre(P(x), P(torch.full_like(x, 441.0)), P(y), ctypes.c_long(n))
+    assert _neq(y, x / 441.0) == 0
+
+
 def test_large_argument_sincos(voice_shim):
     """Phases reach 3e5 rad (4 s) / 2.4e6 rad (30 s): the reduction must keep relative accuracy near sin's zeros."""
     g = torch.Generator().manual_seed(7)
