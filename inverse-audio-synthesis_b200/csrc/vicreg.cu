@@ -82,6 +82,7 @@ struct RowSrc {
   int rows_per;
 };
 
+// Scalar version: any D, any alignment.
 __global__ void __launch_bounds__(256) k_colsum(RowSrc src, int B, int D, int local_row0, int local_rows,
                                                 float* __restrict__ partial, float* __restrict__ repr,
                                                 float* __restrict__ xg, float* __restrict__ yg) {
@@ -109,6 +110,86 @@ __global__ void __launch_bounds__(256) k_colsum(RowSrc src, int B, int D, int lo
     }
     partial[((size_t)blockIdx.x * 2 + 0) * D + d] = sx;
     partial[((size_t)blockIdx.x * 2 + 1) * D + d] = sy;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rp += __shfl_xor_sync(0xffffffffu, rp, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = rp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    repr[blockIdx.x] = t;
+  }
+}
+
+// 128-bit version (D % 4 == 0, 16-byte aligned rows): the CTA's 128 rows are split over 4 row groups of 64 threads,
+// each thread owns one column quad and keeps 8 independent 16-byte loads in flight per matrix, so the pass runs at
+// memory latency / 8 per row instead of one round trip per row.  Same outputs as k_colsum (the per-column sums add
+// the same values in a different order).
+constexpr int CS_CG = 64;                 // column quads per pass
+constexpr int CS_RG = 256 / CS_CG;        // row groups
+__global__ void __launch_bounds__(256) k_colsum_v4(RowSrc src, int B, int D, int local_row0, int local_rows,
+                                                   float* __restrict__ partial, float* __restrict__ repr,
+                                                   float* __restrict__ xg, float* __restrict__ yg) {
+  __shared__ float4 s_part[2][CS_RG][CS_CG];
+  __shared__ float s_red[8];
+  const int r0 = blockIdx.x * COLSUM_ROWS;
+  const int r1 = min(r0 + COLSUM_ROWS, B);
+  const int cg = threadIdx.x % CS_CG, rg = threadIdx.x / CS_CG;
+  const int D4 = D / 4;
+  // rows of one CTA normally belong to one rank (rows_per % 128 == 0): resolve the peer once
+  const int q0 = r0 / src.rows_per;
+  const bool one_peer = (r1 - 1) / src.rows_per == q0;
+  float rp = 0.0f;
+  for (int c0 = 0; c0 < D4; c0 += CS_CG) {
+    const int c4 = c0 + cg;
+    float4 sx = make_float4(0.f, 0.f, 0.f, 0.f), sy = sx;
+    if (c4 < D4) {
+      constexpr int U = 8;
+      for (int rb = r0 + rg; rb < r1; rb += CS_RG * U) {
+        float4 a[U], c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = rb + u * CS_RG;
+          if (r < r1) {
+            const int q = one_peer ? q0 : r / src.rows_per;
+            const size_t lo = (size_t)(r - q * src.rows_per) * D4 + c4;
+            // plain (coherent) loads: the peers' buffers were written by other GPUs just before the barrier
+            a[u] = reinterpret_cast<const float4*>(src.x[q])[lo];
+            c[u] = reinterpret_cast<const float4*>(src.y[q])[lo];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = rb + u * CS_RG;
+          if (r < r1) {
+            if (xg) {  // fused all-gather: keep a local copy of the gathered batch for the passes that follow
+              reinterpret_cast<float4*>(xg)[(size_t)r * D4 + c4] = a[u];
+              reinterpret_cast<float4*>(yg)[(size_t)r * D4 + c4] = c[u];
+            }
+            sx.x += a[u].x; sx.y += a[u].y; sx.z += a[u].z; sx.w += a[u].w;
+            sy.x += c[u].x; sy.y += c[u].y; sy.z += c[u].z; sy.w += c[u].w;
+            if (r >= local_row0 && r < local_row0 + local_rows) {
+              const float e0 = a[u].x - c[u].x, e1 = a[u].y - c[u].y, e2 = a[u].z - c[u].z, e3 = a[u].w - c[u].w;
+              rp = fmaf(e0, e0, rp); rp = fmaf(e1, e1, rp); rp = fmaf(e2, e2, rp); rp = fmaf(e3, e3, rp);
+            }
+          }
+        }
+      }
+    }
+    s_part[0][rg][cg] = sx;
+    s_part[1][rg][cg] = sy;
+    __syncthreads();
+    if (rg < 2 && c4 < D4) {  // row group 0 finishes x, row group 1 finishes y
+      float4 t = s_part[rg][0][cg];
+#pragma unroll
+      for (int g = 1; g < CS_RG; ++g) {
+        const float4 v = s_part[rg][g][cg];
+        t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+      }
+      reinterpret_cast<float4*>(partial + ((size_t)blockIdx.x * 2 + rg) * D)[c4] = t;
+    }
+    __syncthreads();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rp += __shfl_xor_sync(0xffffffffu, rp, o);
@@ -696,8 +777,13 @@ RowSrc single_src(const float* x, const float* y, int B) {
 int run_stats_and_gram(const RowSrc& src, const float* x, const float* y, float* xg, float* yg, const Plan& p,
                        int local_row0, int B_local, float* w, float* gram_full, cudaStream_t st) {
   {
+    bool v4 = (p.D % 4 == 0) && ias_aligned16(xg) && ias_aligned16(yg);
+    for (int q = 0; q < MAX_PEERS; ++q) v4 = v4 && ias_aligned16(src.x[q]) && ias_aligned16(src.y[q]);
     ProfScope prof_(K_VICREG_COLSUM, st);
-    k_colsum<<<p.P, 256, 0, st>>>(src, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr, xg, yg);
+    if (v4)
+      k_colsum_v4<<<p.P, 256, 0, st>>>(src, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr, xg, yg);
+    else
+      k_colsum<<<p.P, 256, 0, st>>>(src, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr, xg, yg);
   }
   IAS_LAUNCH_CHECK("k_colsum");
   {

@@ -12,7 +12,7 @@ for f in pqmf vicreg voice e2e; do
 done
 timeout 900 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"; cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err; echo "ref exit $?"
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-graph"
 timeout 300 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "ncu launch list exit $?"
@@ -23,3 +23,4 @@ for K in k_pqmf_analysis k_gram_tc k_voice_control; do
   echo "ncu $K exit $?"
 done
 ls -la gpurun_out | head -40
+timeout 600 python tools/bench_configs.py > gpurun_out/configs_$TAG.jsonl 2> gpurun_out/configs_$TAG.err; echo "configs exit $?"
