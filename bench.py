@@ -338,10 +338,9 @@ def run_ours(args):
     e2e_last = [float(v) for v in host_out]
 
     # ---- variant: parameters supplied by the host (pinned [78,B] block copied in every step, seeding skipped) ----
-    host_params = torch.rand((78, B)).pin_memory()
-    sync()
-    e0.record()
-    for j in range(args.steps):
+    host_params = torch.rand((78, B), generator=torch.Generator().manual_seed(4321)).pin_memory()
+
+    def step_host_params():
         voice._store.copy_(host_params, non_blocking=True)
         audio = voice.output()
         bands = gram(audio.unsqueeze(1))
@@ -349,6 +348,13 @@ def run_ours(args):
         with torch.no_grad():
             o = vic.loss(x, y)
         host_out.copy_(torch.stack(o))
+
+    for j in range(3):  # warm-up: the eager path allocates its own audio / band buffers (the graphs own theirs)
+        step_host_params()
+    sync()
+    e0.record()
+    for j in range(args.steps):
+        step_host_params()
     e1.record()
     sync()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)

@@ -125,16 +125,45 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 // k_voice_control
 // ------------------------------------------------------------------------------------------------------------
 constexpr int CTRL_THREADS = 256;
+#ifndef IAS_CTRL_MINB
+#define IAS_CTRL_MINB 2
+#endif
 constexpr int REC_FLOATS = 16;  // floats per control-interval record (4 x 16-byte loads in the audio stage)
 
 struct ControlShared {
   float P[NROWS];
-  Adsr adsr[6];  // adsr_1, adsr_2, lfo_1_amp, lfo_2_amp, lfo_1_rate, lfo_2_rate
   Lfo lfo[2];
   ModMatrix mm;
   double wsum[2][CTRL_THREADS / 32];
   int last_nz[CTRL_THREADS / 32];
 };
+
+// ------------------------------------------------------------------------------------------------------------
+// k_voice_adsr: the six envelopes of every voice, one CTA per (envelope, voice): env[b][e][j], e in the order
+// adsr_1, adsr_2, lfo_1_amp_adsr, lfo_2_amp_adsr, lfo_1_rate_adsr, lfo_2_rate_adsr.  This is where the SLEEF-exact
+// pow lives (~300 dependent instructions, ~3.5 live per control point and voice); as its own kernel it needs < 64
+// registers, so 2.5x more warps are resident to hide the dependency chains than inside the control kernel.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ADSR_THREADS = 128;
+
+__global__ void __launch_bounds__(ADSR_THREADS, 8)
+k_voice_adsr(const float* __restrict__ params01, int B, int C, float cr, float eps, RangeTable ranges,
+             float* __restrict__ env) {
+  __shared__ float s_v[6];  // attack, decay, sustain, release, alpha, keyboard duration (through from_0to1)
+  __shared__ Adsr s_adsr;
+  const int e = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int base[6] = {ADSR1, ADSR2, LFO1_AMP, LFO2_AMP, LFO1_RATE, LFO2_RATE};
+  if (tid < 6) {
+    const int row = tid < 5 ? base[e] + tid : (int)KEY_DURATION;
+    s_v[tid] = from_0to1(params01[(size_t)row * B + b], ranges.r[row]);
+  }
+  __syncthreads();
+  if (tid < 3) adsr_setup_part(s_adsr, tid, s_v, s_v[5], cr, eps, C);
+  __syncthreads();
+  float* out = env + ((size_t)b * 6 + e) * C;
+  for (int j = tid; j < C; j += ADSR_THREADS) out[j] = adsr_eval(s_adsr, (float)j, eps);
+}
 
 // Per-interval record j of one voice, read by the audio-stage threads whose samples start in control interval j:
 //   [0..2]  vco_1_pitch at points j, j+1, j+2 (clamped to C-1)      exact values: they feed the phase
@@ -142,14 +171,16 @@ struct ControlShared {
 //   [6..8]  AmpLine of vco_1_amp  * mixer level 1
 //   [9..11] AmpLine of vco_2_amp  * mixer level 2 * (1 - shape/2)
 //   [12..14] AmpLine of noise_amp * mixer level 3
-// Measured (r01j, 1024 voices): pow out of line + 2 CTAs/SM 0.191 ms; inlined 0.219; 3 CTAs/SM spills: 0.224-0.259.
-#ifndef IAS_CTRL_MINB
-#define IAS_CTRL_MINB 2
-#endif
+// `env` holds the six envelopes (k_voice_adsr).  SMEM: the two LFO phase rows and the five output rows of the voice
+// live in shared memory (7*C floats: 4 s clips), so the dependent phases never wait on global memory; otherwise
+// (30 s clips: 370 KB) the phase rows are built in place in `env` and the output rows in `ctrl_ws`.
+// ctrl_out (may be null) receives the five signals [B][5][C] for inspection.
+template <bool SMEM>
 __global__ void __launch_bounds__(CTRL_THREADS, IAS_CTRL_MINB)
 k_voice_control(const float* __restrict__ params01, int B, int C, float cr, float eps, RangeTable ranges,
-                const float* __restrict__ ctrl_in, float* __restrict__ ctrl, float* __restrict__ scratch,
-                float* __restrict__ vconst, float4* __restrict__ rec) {
+                const float* __restrict__ ctrl_in, float* __restrict__ ctrl_out, float* __restrict__ ctrl_ws,
+                float* __restrict__ env_all, float* __restrict__ vconst, float4* __restrict__ rec) {
+  extern __shared__ __align__(16) float s_rows[];
   __shared__ ControlShared sh;
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -157,32 +188,27 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
 
   if (tid < NROWS) sh.P[tid] = from_0to1(params01[(size_t)tid * B + b], ranges.r[tid]);
   __syncthreads();
-  // per-voice setup, one item per thread of four different warps so the serial pow / division chains overlap
-  if (tid < 18) {  // 6 envelopes x {attack, decay, release}
-    const int base[6] = {ADSR1, ADSR2, LFO1_AMP, LFO2_AMP, LFO1_RATE, LFO2_RATE};
-    adsr_setup_part(sh.adsr[tid / 3], tid % 3, &sh.P[base[tid / 3]], sh.P[KEY_DURATION], cr, eps, C);
-  } else if (tid >= 32 && tid < 34) {
-    sh.lfo[tid - 32] = lfo_setup(&sh.P[tid == 32 ? LFO1 : LFO2]);
-  } else if (tid == 64) {
+  // per-voice setup, one item per thread of different warps so the serial pow / division chains overlap
+  if (tid < 10) {  // the five mode weights of each LFO: w ** e
+    sh.lfo[tid / 5].w[tid % 5] = pow_sleef(sh.P[(tid < 5 ? LFO1 : LFO2) + 3 + tid % 5], 2.718281828f);
+  } else if (tid == 32) {
     sh.mm = modmatrix_setup(&sh.P[MODM]);
-  } else if (tid == 96) {
+  } else if (tid == 64) {
     voice_constants(sh.P, vconst + (size_t)b * VC_COUNT);
   }
   __syncthreads();
+  if (tid < 2) lfo_finish(sh.lfo[tid], &sh.P[tid == 0 ? LFO1 : LFO2]);
+  __syncthreads();
 
-  float* sc = scratch + (size_t)b * 6 * C;  // [6][C]: x1|arg1, x2|arg2, amp1, amp2, adsr_1, adsr_2
-  // Phase A: pointwise envelopes and LFO phase increments
+  float* env = env_all + (size_t)b * 6 * C;  // [6][C]: adsr_1, adsr_2, lfo_1 amp, lfo_2 amp, lfo_1 rate, lfo_2 rate
+  float* ph0 = SMEM ? s_rows : env + 4 * C;
+  float* ph1 = SMEM ? s_rows + C : env + 5 * C;
+  float* out = SMEM ? s_rows + 2 * C : ctrl_ws + (size_t)b * IAS_VOICE_NCONTROL * C;
+  // Phase A: LFO phase increments from the rate envelopes
   const float rcr = rcp(cr);
   for (int j = tid; j < C; j += CTRL_THREADS) {
-    float n = (float)j;
-    float rate1 = adsr_eval(sh.adsr[4], n, eps);
-    float rate2 = adsr_eval(sh.adsr[5], n, eps);
-    sc[0 * C + j] = lfo_increment(sh.lfo[0], rate1, cr, rcr);
-    sc[1 * C + j] = lfo_increment(sh.lfo[1], rate2, cr, rcr);
-    sc[2 * C + j] = adsr_eval(sh.adsr[2], n, eps);
-    sc[3 * C + j] = adsr_eval(sh.adsr[3], n, eps);
-    sc[4 * C + j] = adsr_eval(sh.adsr[0], n, eps);
-    sc[5 * C + j] = adsr_eval(sh.adsr[1], n, eps);
+    ph0[j] = lfo_increment(sh.lfo[0], env[4 * C + j], cr, rcr);
+    ph1[j] = lfo_increment(sh.lfo[1], env[5 * C + j], cr, rcr);
   }
   __syncthreads();
 
@@ -191,8 +217,8 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
   const int j0 = min(tid * chunk, C), j1 = min(j0 + chunk, C);
   double tot[2] = {0.0, 0.0};
   for (int j = j0; j < j1; ++j) {
-    tot[0] += (double)sc[0 * C + j];
-    tot[1] += (double)sc[1 * C + j];
+    tot[0] += (double)ph0[j];
+    tot[1] += (double)ph1[j];
   }
   double pre[2];
 #pragma unroll
@@ -207,23 +233,28 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
     double acc = pre[l];
     for (int w = 0; w < warp; ++w) acc += sh.wsum[l][w];
     const float phase0 = sh.lfo[l].initial_phase;
+    float* ph = l ? ph1 : ph0;
     for (int j = j0; j < j1; ++j) {
-      acc += (double)sc[l * C + j];
-      sc[l * C + j] = add((float)acc, phase0);
+      acc += (double)ph[j];
+      ph[j] = add((float)acc, phase0);
     }
   }
   __syncthreads();
 
   // Phase C: LFO shapes, VCAs, modulation matrix
-  float* out = ctrl + (size_t)b * IAS_VOICE_NCONTROL * C;
+  float* user = ctrl_out ? ctrl_out + (size_t)b * IAS_VOICE_NCONTROL * C : nullptr;
   for (int j = tid; j < C; j += CTRL_THREADS) {
-    float l1 = mul(lfo_shapes_mix(sh.lfo[0], sc[0 * C + j]), sc[2 * C + j]);
-    float l2 = mul(lfo_shapes_mix(sh.lfo[1], sc[1 * C + j]), sc[3 * C + j]);
-    float a1 = sc[4 * C + j], a2 = sc[5 * C + j];
+    float l1 = mul(lfo_shapes_mix(sh.lfo[0], ph0[j]), env[2 * C + j]);
+    float l2 = mul(lfo_shapes_mix(sh.lfo[1], ph1[j]), env[3 * C + j]);
+    float a1 = env[0 * C + j], a2 = env[1 * C + j];
 #pragma unroll
-    for (int o = 0; o < 5; ++o) out[o * C + j] = modmatrix_out(sh.mm, o, a1, a2, l1, l2);
+    for (int o = 0; o < 5; ++o) {
+      const float v = modmatrix_out(sh.mm, o, a1, a2, l1, l2);
+      out[o * C + j] = v;
+      if (user) user[o * C + j] = v;
+    }
   }
-  __syncthreads();  // this CTA's ctrl rows are re-read below
+  __syncthreads();  // this CTA's output rows are re-read below
 
   // Phase D: per-interval records for the audio stage (from the caller's signals when the parity hook supplies them)
   const float* src = ctrl_in ? ctrl_in + (size_t)b * IAS_VOICE_NCONTROL * C : out;
@@ -568,13 +599,30 @@ VoiceWorkspace carve(void* ws, int B, int C) {
   return w;
 }
 
-int launch_control(const float* params01, int B, int C, float cr, float eps, const float* ctrl_in,
+int launch_control(const float* params01, int B, int C, float cr, float eps, const float* ctrl_in, float* ctrl_out,
                    const VoiceWorkspace& w, cudaStream_t st) {
   static const RangeTable ranges = make_range_table();
   {
+    ProfScope prof_(K_VOICE_ADSR, st);
+    k_voice_adsr<<<dim3(6, B), ADSR_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, w.scratch);
+  }
+  IAS_LAUNCH_CHECK("k_voice_adsr");
+  {
+    // 4 s clips: phase + output rows in shared memory (7*C floats); longer clips fall back to global scratch rows
+    const size_t smem = (size_t)7 * C * sizeof(float);
+    static bool attr_set = false;
+    constexpr size_t SMEM_LIMIT = 100 * 1024;  // two CTAs per SM
+    if (!attr_set) {
+      IAS_CUDA(cudaFuncSetAttribute(k_voice_control<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+      attr_set = true;
+    }
     ProfScope prof_(K_VOICE_CONTROL, st);
-    k_voice_control<<<B, CTRL_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, ctrl_in, w.ctrl, w.scratch, w.vconst,
-                                                w.rec);
+    if (smem <= SMEM_LIMIT)
+      k_voice_control<true><<<B, CTRL_THREADS, smem, st>>>(params01, B, C, cr, eps, ranges, ctrl_in, ctrl_out, w.ctrl,
+                                                           w.scratch, w.vconst, w.rec);
+    else
+      k_voice_control<false><<<B, CTRL_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, ctrl_in, ctrl_out, w.ctrl,
+                                                         w.scratch, w.vconst, w.rec);
   }
   IAS_LAUNCH_CHECK("k_voice_control");
   return IAS_OK;
@@ -708,11 +756,7 @@ extern "C" int ias_voice_control(const float* params01, int B, int C, float cont
               "ias_voice_control: workspace %zu < %zu bytes", workspace_bytes, ias_voice_workspace_bytes(B, 0, C));
   IAS_REQUIRE(ias_aligned16(workspace), IAS_ERR_INVALID, "ias_voice_control: workspace must be 16-byte aligned");
   VoiceWorkspace w = carve(workspace, B, C);
-  int rc = launch_control(params01, B, C, control_rate, eps, nullptr, w, as_stream(stream));
-  if (rc) return rc;
-  IAS_CUDA(cudaMemcpyAsync(ctrl, w.ctrl, (size_t)B * IAS_VOICE_NCONTROL * C * sizeof(float),
-                           cudaMemcpyDeviceToDevice, as_stream(stream)));
-  return IAS_OK;
+  return launch_control(params01, B, C, control_rate, eps, nullptr, ctrl, w, as_stream(stream));
 }
 
 extern "C" int ias_voice_render(const float* params01, const float* noise, int noise_rows, float* audio, float* peak,
@@ -731,7 +775,7 @@ extern "C" int ias_voice_render(const float* params01, const float* noise, int n
   IAS_REQUIRE(ias_aligned16(workspace), IAS_ERR_INVALID, "ias_voice_render: workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   VoiceWorkspace w = carve(workspace, B, C);
-  int rc = launch_control(params01, B, C, control_rate, eps, ctrl_in, w, st);
+  int rc = launch_control(params01, B, C, control_rate, eps, ctrl_in, nullptr, w, st);
   if (rc) return rc;
   AudioArgs a;
   a.rec = w.rec;

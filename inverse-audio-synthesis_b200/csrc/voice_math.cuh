@@ -427,6 +427,17 @@ IAS_HD Lfo lfo_setup(const float* v) {
   return l;
 }
 
+// The same in two steps, so the five pows can be spread over threads: the caller fills l.w[i] = v[3+i] ** e first.
+IAS_HD void lfo_finish(Lfo& l, const float* v) {
+  l.frequency = v[0];
+  l.mod_depth = v[1];
+  l.initial_phase = v[2];
+  float s = add(add(add(add(l.w[0], l.w[4]), l.w[1]), l.w[2]), l.w[3]);
+  float m[5];
+  for (int i = 0; i < 5; ++i) m[i] = l.w[i];
+  for (int i = 0; i < 5; ++i) l.w[i] = div(m[i], s);
+}
+
 // phase increment of one control sample: 2*pi*max(frequency + mod_depth*mod, 0) / control_rate
 IAS_HD float lfo_increment(const Lfo& l, float mod, float cr) {
   float f = fmaxf(add(l.frequency, mul(l.mod_depth, mod)), 0.0f);
