@@ -206,3 +206,40 @@ def test_render_rejects_bad_arguments(cuda_device):
     rc = lib.ias_voice_render(_lib.ptr(p), _lib.ptr(noise), 32, _lib.ptr(audio), None, 32, 800, 400, 44100.0, 441.0,
                               1e-6, 1, None, None, _lib.ptr(ws), ws.numel(), _lib.current_stream(cuda_device))
     assert rc == 3 and b"audio samples per control sample" in lib.ias_last_error()
+
+
+def test_sound_id_determines_audio_regardless_of_batch_size(cuda_device):
+    """Size-independent property: sound id -> same parameters -> same audio, whatever the batch size.
+    A 2080-voice batch also exercises the work queue with more voices than resident CTAs and the longest-first order;
+    the 32-voice renders of the same ids must match it bit for bit (same kernel shape => same rounding)."""
+    big_B, small_B = 2080, 32
+    big = _voice(cuda_device, B=big_B, seconds=0.5, reproducible=False)
+    # non-reproducible noise is per row: give every small batch the matching rows of the big table
+    audio_big, params_big, train_big = big(0)
+    for chunk in (0, 17, 64):
+        small = _voice(cuda_device, B=small_B, seconds=0.5, reproducible=False)
+        small.noise.noise.copy_(big.noise.noise[chunk * small_B:(chunk + 1) * small_B])
+        a, p, t = small(chunk)
+        sl = slice(chunk * small_B, (chunk + 1) * small_B)
+        assert torch.equal(p, params_big[sl]) and torch.equal(t, train_big[sl])
+        assert torch.equal(a, audio_big[sl])
+    assert torch.isfinite(audio_big).all() and float(audio_big.abs().max()) <= 1.0 + 1e-6
+
+
+def test_all_silent_and_single_voice_batches(cuda_device):
+    """Edge cases: voices whose three mixer levels are 0 render exact zeros (peak 0, no normalisation by 0), and
+    B = 1 runs with a one-CTA grid on the scalar (T % 8 != 0) path."""
+    B = 32
+    voice = _voice(cuda_device, B=B, seconds=0.25, reproducible=False)
+    voice.randomize(seed=5)
+    for name in ("vco_1", "vco_2", "noise"):
+        level = voice.mixer.get_parameter_0to1(name).clone()
+        level[::2] = 0.0
+        voice.mixer.set_parameter_0to1(name, level)
+    audio, peak = voice.output(return_peak=True)
+    assert float(audio[::2].abs().max()) == 0.0 and float(peak[::2].abs().max()) == 0.0
+    assert float(audio[1::2].abs().max()) > 0.0
+    one = _voice(cuda_device, B=1, seconds=0.25, reproducible=False)
+    a1, p1, _ = one(7)
+    ref = V.voice_render(V.seeded_params(7, 1), one.noise.noise.cpu(), 11025, 110)["audio"]
+    assert a1.shape == (1, 11025) and float((a1.cpu() - ref).abs().max()) <= 5e-3
