@@ -12,6 +12,8 @@
 // HBM traffic: 4T read + 4T written per sound in each direction (algorithmic minimum).
 #include "ias_common.cuh"
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace ias {
@@ -481,12 +483,19 @@ extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const floa
   IAS_REQUIRE(G_dev || G_host, IAS_ERR_INVALID, "ias_pqmf_synthesis: no filter given");
   cudaStream_t st = as_stream(stream);
   if (G_host && K == 63) {
+    int q = 0;  // IAS_PQMF_SYNTH_Q: tuning override of the time steps per thread
+    if (const char* e = getenv("IAS_PQMF_SYNTH_Q")) q = atoi(e);
     switch (N) {
       case 2: return launch_synthesis<2, 63, 8>(z, G_host, y, B, L, st);
-      case 3: return launch_synthesis<3, 63, 8>(z, G_host, y, B, L, st);
+      case 3:
+        if (q == 16) return launch_synthesis<3, 63, 16>(z, G_host, y, B, L, st);
+        if (q == 8) return launch_synthesis<3, 63, 8>(z, G_host, y, B, L, st);
+        return launch_synthesis<3, 63, 4>(z, G_host, y, B, L, st);  // measured: Q=4 0.495 ms, Q=8 0.527, Q=16 0.668
       case 4: return launch_synthesis<4, 63, 8>(z, G_host, y, B, L, st);
       case 8: return launch_synthesis<8, 63, 4>(z, G_host, y, B, L, st);
-      case 16: return launch_synthesis<16, 63, 2>(z, G_host, y, B, L, st);
+      case 16:
+        if (q == 4) return launch_synthesis<16, 63, 4>(z, G_host, y, B, L, st);
+        return launch_synthesis<16, 63, 2>(z, G_host, y, B, L, st);
       default: break;
     }
   }
