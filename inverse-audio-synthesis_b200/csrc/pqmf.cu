@@ -43,18 +43,18 @@ struct BandNorm {
   int on;
 };
 
-__host__ __device__ constexpr int odd_stride(int s) { return (s & 1) ? s : s + 1; }
 
-// Shared-memory layout of a staged signal row.  Thread t reads a sliding window that starts at linear index t*S, so
-// rows are stored in chunks of S floats at a padded pitch SP chosen to keep those reads bank-conflict free:
-//   S % 4 == 0: SP is a multiple of 4 with SP/4 odd -> 128-bit loads/stores, the 8 lanes of a quarter warp hit 8
-//               distinct 16-byte bank groups;  otherwise: SP odd, 32-bit accesses.
+// Shared-memory layout of a staged signal row.  Thread t reads a sliding window that starts at linear index t*S.
+//   S % 4 == 0: rows are stored in chunks of S floats at a padded pitch SP (a multiple of 4 with SP/4 odd), so the
+//               128-bit window loads of a quarter warp hit 8 distinct 16-byte bank groups;
+//   otherwise (S = 2: N = 16 synthesis): plain linear layout.  Staging stays a 128-bit copy with no index arithmetic;
+//               the scalar window loads see a 2-way bank conflict, on ~80 loads per thread against ~2000 FMAs.
 template <int S>
 struct Pad {
   static constexpr bool VEC = (S % 4 == 0);
-  static constexpr int SP = VEC ? ((((S / 4) & 1) == 1) ? S : S + 4) : odd_stride(S);
-  __host__ __device__ static constexpr int at(int i) { return (i / S) * SP + (i % S); }
-  __host__ __device__ static constexpr int floats(int span) { return (span / S + 2) * SP; }
+  static constexpr int SP = VEC ? ((((S / 4) & 1) == 1) ? S : S + 4) : S;
+  __host__ __device__ static constexpr int at(int i) { return VEC ? (i / S) * SP + (i % S) : i; }
+  __host__ __device__ static constexpr int floats(int span) { return VEC ? (span / S + 2) * SP : span + 8; }
 };
 
 // Stage `SPAN4` float4 groups of one row into shared memory: global index g0 + 4*i4 (g0 % 4 == 0), zero outside
@@ -86,9 +86,7 @@ __device__ __forceinline__ void stage_row(float* __restrict__ dst, const float* 
         ++q;
       }
     } else {
-      const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) dst[P::at(4 * i4 + c)] = e[c];
+      *reinterpret_cast<float4*>(dst + 4 * i4) = v;  // linear layout
     }
   }
 }
@@ -108,14 +106,7 @@ __device__ __forceinline__ void stage_row_interior(float* __restrict__ dst, cons
   for (int i = 0; i < ITERS; ++i)
     if ((i + 1) * PQ_THREADS <= SPAN4 || (int)threadIdx.x + i * PQ_THREADS < SPAN4) {
       const int i4 = (int)threadIdx.x + i * PQ_THREADS;
-      if constexpr (P::VEC) {
-        *reinterpret_cast<float4*>(dst + P::at(4 * i4)) = v[i];
-      } else {
-        dst[P::at(4 * i4 + 0)] = v[i].x;
-        dst[P::at(4 * i4 + 1)] = v[i].y;
-        dst[P::at(4 * i4 + 2)] = v[i].z;
-        dst[P::at(4 * i4 + 3)] = v[i].w;
-      }
+      *reinterpret_cast<float4*>(dst + P::at(4 * i4)) = v[i];  // linear layout when !VEC: at() is the identity
     }
 }
 
