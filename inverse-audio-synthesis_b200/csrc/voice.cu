@@ -369,6 +369,125 @@ struct AudioArgs {
   int normalize;
 };
 
+// ---- packed fp32 (sm_100: FFMA2 / FADD2 / FMUL2 process two fp32 lanes per instruction) --------------------------
+// The audio kernel is bound by instruction issue, and 2/3 of its instructions are fp32 arithmetic: evaluating two
+// adjacent samples per packed instruction halves those issue slots.  Each lane is an IEEE round-to-nearest fp32
+// operation, so results are bit-identical to the scalar helpers in voice_math.cuh.  One caveat, measured with
+// cuobjdump: ptxas contracts mul.rn.f32x2 feeding add/sub.rn.f32x2 into FFMA2 even with --fmad=false, so wherever the
+// reference rounds a product before adding to it, one of the two operations is issued in scalar form (which ptxas
+// never contracts).  tests/test_gpu_voice.py compares every phase argument bit for bit against the torch CPU path.
+struct P2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ P2 p2(float lo, float hi) {
+  P2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ P2 p2b(float a) { return p2(a, a); }  // broadcast (a scalar / immediate operand in SASS)
+__device__ __forceinline__ float p2lo(P2 a) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  return x;
+}
+__device__ __forceinline__ float p2hi(P2 a) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  return y;
+}
+__device__ __forceinline__ P2 p2_fma(P2 a, P2 b, P2 c) {
+  P2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ P2 p2_add(P2 a, P2 b) {
+  P2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ P2 p2_sub(P2 a, P2 b) {
+  P2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
+  P2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+
+// vm::vco_increment for two samples: 2*pi*hz(clamp(midi + depth*mod, 0, 127)) / sample_rate, same op order.
+__device__ __forceinline__ P2 vco_increment_p2(float midi, float depth, P2 mod, float sr, float rsr) {
+  const P2 dm = p2_mul(p2b(depth), mod);
+  // scalar adds: the product keeps its own rounding (see the note on contraction above)
+  const float m0 = fminf(fmaxf(add(midi, p2lo(dm)), 0.0f), 127.0f);
+  const float m1 = fminf(fmaxf(add(midi, p2hi(dm)), 0.0f), 127.0f);
+  const P2 a = p2_add(p2(m0, m1), p2b(-69.0f));
+  // a / 12: Markstein step with RN(1/12)  (div_const)
+  const P2 q = p2_mul(a, p2b(0.0833333358168601989746f));
+  const P2 d = p2_fma(p2_fma(q, p2b(-12.0f), a), p2b(0.0833333358168601989746f), q);
+  // exp2_fast
+  const float magic = 12582912.0f;
+  const P2 t = p2_add(d, p2b(magic));
+  const P2 sfrac = p2_sub(d, p2_add(t, p2b(-magic)));
+  P2 u = p2b(+0.1535920892e-3f);
+  u = p2_fma(u, sfrac, p2b(+0.1339262701e-2f));
+  u = p2_fma(u, sfrac, p2b(+0.9618384764e-2f));
+  u = p2_fma(u, sfrac, p2b(+0.5550347269e-1f));
+  u = p2_fma(u, sfrac, p2b(+0.2402264476e+0f));
+  u = p2_fma(u, sfrac, p2b(+0.6931471825e+0f));
+  u = p2_fma(u, sfrac, p2b(1.0f));
+  // exponent add: (bits(t) - 0x4B400000) << 23 == bits(t) << 23 (the magic's low 9 bits are zero)
+  const float e0 = i2f(f2i(p2lo(u)) + (f2i(p2lo(t)) << 23));
+  const float e1 = i2f(f2i(p2hi(u)) + (f2i(p2hi(t)) << 23));
+  const P2 w = p2_mul(p2b(IAS_TWO_PI_F), p2_mul(p2b(440.0f), p2(e0, e1)));
+  // w / sr: Markstein step with RN(1/sr)
+  const P2 qq = p2_mul(w, p2b(rsr));
+  return p2_fma(p2_fma(qq, p2b(-sr), w), p2b(rsr), qq);
+}
+
+// vm::reduce_half_turns for two arguments: a = (n + f) * pi, f in [-0.5, 0.5]; t carries n in its low mantissa bits.
+__device__ __forceinline__ void reduce_half_turns_p2(P2 a, P2& f, P2& t) {
+  const float C1 = 0.318309873342514038f;
+  const float C2 = (float)(0.31830988618379067154 - (double)0.318309873342514038f);
+  const float magic = 12582912.0f;
+  t = p2_fma(a, p2b(C1), p2b(magic));
+  const P2 nneg = p2_sub(p2b(magic), t);  // -rint(a / pi)
+  f = p2_fma(a, p2b(C2), p2_fma(a, p2b(C1), nneg));
+}
+__device__ __forceinline__ float flip_sign(float v, float t) { return i2f(f2i(v) ^ (f2i(t) << 31)); }
+// cos(pi * f) of both lanes through the SFU, sign flipped by the parity of n
+__device__ __forceinline__ P2 cospi_p2(P2 f, P2 t) {
+  const P2 fr = p2_mul(f, p2b(IAS_PI_F));
+  return p2(flip_sign(__cosf(p2lo(fr)), p2lo(t)), flip_sign(__cosf(p2hi(fr)), p2hi(t)));
+}
+__device__ __forceinline__ P2 cos_arg_p2(P2 a) {
+  P2 f, t;
+  reduce_half_turns_p2(a, f, t);
+  return cospi_p2(f, t);
+}
+// vm::squaresaw_core for two arguments
+__device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
+  P2 f, t;
+  reduce_half_turns_p2(a, f, t);
+  const P2 u = p2_mul(f, f);
+  P2 p = p2b(0.07634329050779343f);
+  p = p2_fma(p, u, p2b(-0.59761643409729f));
+  p = p2_fma(p, u, p2b(2.5499696731567383f));
+  p = p2_fma(p, u, p2b(-5.1677045822143555f));
+  p = p2_fma(p, u, p2b(3.141592502593994f));
+  const P2 sn = p2_mul(p, f);
+  const P2 sc = p2_mul(p2b(pk), p2(flip_sign(p2lo(sn), p2lo(t)), flip_sign(p2hi(sn), p2hi(t))));
+  float e0, e1, r0, r1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(p2lo(sc)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(p2hi(sc)));
+  const P2 ep = p2_add(p2(e0, e1), p2b(1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p2lo(ep)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p2hi(ep)));
+  const P2 th = p2_fma(p2b(-2.0f), p2(r0, r1), p2b(1.0f));
+  return p2_mul(th, p2_fma(p2b(shape), cospi_p2(f, t), p2b(1.0f)));
+}
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Persistent CTAs pull voices from the queue.  Per voice: tiles of NT*SPT samples, SPT consecutive samples per thread.
@@ -425,19 +544,29 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
       const float4 r0 = __ldg(rj + 0);
       const float4 r1 = __ldg(rj + 1);
 #pragma unroll
-      for (int k = 0; k < SPT; ++k) {
-        const float src = mul(scale, add(ft0, (float)k));  // the reference's fp32 source coordinate
-        srcs[k] = src;
-        const bool d = src >= fj1;
-        const float l1 = sub(src, d ? fj1 : fj);  // in [0,1): j = floor(src) of the thread's first sample
-        const float l0 = sub(1.0f, l1);
-        const float m1 = upsample_mix(d ? r0.y : r0.x, d ? r0.z : r0.y, l0, l1);
-        const float m2 = upsample_mix(d ? r1.x : r0.w, d ? r1.y : r1.x, l0, l1);
+      for (int k = 0; k < SPT; k += 2) {  // two samples per packed instruction
+        const P2 fi = p2_add(p2b(ft0), p2((float)k, (float)(k + 1)));
+        // the reference's fp32 source coordinate; scalar products so that they are rounded before the subtraction
+        const float s0 = mul(scale, p2lo(fi)), s1 = mul(scale, p2hi(fi));
+        srcs[k] = s0;
+        srcs[k + 1] = s1;
+        const bool d0 = s0 >= fj1, d1 = s1 >= fj1;
+        const P2 l1 = p2_sub(p2(s0, s1), p2(d0 ? fj1 : fj, d1 ? fj1 : fj));  // in [0,1): j = floor(src) of sample 0
+        const P2 l0 = p2_sub(p2b(1.0f), l1);
+        // upsample_mix: fma(l0, x[i0], l1 * x[i1])
+        const P2 m1 = p2_fma(l0, p2(d0 ? r0.y : r0.x, d1 ? r0.y : r0.x),
+                             p2_mul(l1, p2(d0 ? r0.z : r0.y, d1 ? r0.z : r0.y)));
+        const P2 m2 = p2_fma(l0, p2(d0 ? r1.x : r0.w, d1 ? r1.x : r0.w),
+                             p2_mul(l1, p2(d0 ? r1.y : r1.x, d1 ? r1.y : r1.x)));
+        const P2 i1 = vco_increment_p2(midi1, depth1, m1, A.sr, A.rsr);
+        const P2 i2 = vco_increment_p2(midi2, depth2, m2, A.sr, A.rsr);
         // VEC: T % SPT == 0, so a thread is wholly live or wholly past the end; dead threads sit after every live
         // one in the last tile, and an inclusive scan never feeds later totals into earlier lanes -> no masking.
-        const bool live = VEC || (t0 + k) < T;
-        x1[k] = live ? vco_increment(midi1, depth1, m1, A.sr, A.rsr) : 0.0f;
-        x2[k] = live ? vco_increment(midi2, depth2, m2, A.sr, A.rsr) : 0.0f;
+        const bool live0 = VEC || (t0 + k) < T, live1 = VEC || (t0 + k + 1) < T;
+        x1[k] = live0 ? p2lo(i1) : 0.0f;
+        x1[k + 1] = live1 ? p2hi(i1) : 0.0f;
+        x2[k] = live0 ? p2lo(i2) : 0.0f;
+        x2[k + 1] = live1 ? p2hi(i2) : 0.0f;
       }
       // ---- block scan -------------------------------------------------------------------------------------
       double tot1 = 0.0, tot2 = 0.0;
@@ -486,22 +615,38 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
       // ---- pass 2: oscillators, VCA gains, noise, mix --------------------------------------------------------
       float y[SPT];
 #pragma unroll
-      for (int k = 0; k < SPT; ++k) {
-        const float u = sub(srcs[k], fj);
-        const float r = fmaxf(sub(srcs[k], fj1), 0.0f);
+      for (int k = 0; k < SPT; k += 2) {
+        const P2 sp = p2(srcs[k], srcs[k + 1]);
+        const P2 u = p2_sub(sp, p2b(fj));
+        const P2 um = p2_sub(sp, p2b(fj1));
+        const P2 r = p2(fmaxf(p2lo(um), 0.0f), fmaxf(p2hi(um), 0.0f));
         acc1 += (double)x1[k];
+        const float a10 = (float)acc1;
+        acc1 += (double)x1[k + 1];
+        const float a11 = (float)acc1;
         acc2 += (double)x2[k];
-        const float arg1 = add((float)acc1, phase1);
-        const float arg2 = add((float)acc2, phase2);
-        const float g1 = fma(r, r2.x, fma(u, r1.w, r1.z));
-        const float g2 = fma(r, r2.w, fma(u, r2.z, r2.y));
-        const float g3 = fma(r, r3.z, fma(u, r3.y, r3.x));
-        y[k] = fma(cos_arg(arg1), g1, fma(squaresaw_core(arg2, pk, shape), g2, mul(nzv[k], g3)));
+        const float a20 = (float)acc2;
+        acc2 += (double)x2[k + 1];
+        const float a21 = (float)acc2;
+        const P2 arg1 = p2_add(p2(a10, a11), p2b(phase1));
+        const P2 arg2 = p2_add(p2(a20, a21), p2b(phase2));
+        const P2 g1 = p2_fma(r, p2b(r2.x), p2_fma(u, p2b(r1.w), p2b(r1.z)));
+        const P2 g2 = p2_fma(r, p2b(r2.w), p2_fma(u, p2b(r2.z), p2b(r2.y)));
+        const P2 g3 = p2_fma(r, p2b(r3.z), p2_fma(u, p2b(r3.y), p2b(r3.x)));
+        const P2 yy = p2_fma(cos_arg_p2(arg1), g1,
+                             p2_fma(squaresaw_core_p2(arg2, pk, shape), g2, p2_mul(p2(nzv[k], nzv[k + 1]), g3)));
+        y[k] = p2lo(yy);
+        y[k + 1] = p2hi(yy);
         if (VEC || (t0 + k) < T) tpeak = fmaxf(tpeak, fabsf(y[k]));
+        if (VEC || (t0 + k + 1) < T) tpeak = fmaxf(tpeak, fabsf(y[k + 1]));
         if (DBG) {
           if ((t0 + k) < T) {
-            A.phase_dbg[((size_t)b * 2 + 0) * T + t0 + k] = arg1;
-            A.phase_dbg[((size_t)b * 2 + 1) * T + t0 + k] = arg2;
+            A.phase_dbg[((size_t)b * 2 + 0) * T + t0 + k] = p2lo(arg1);
+            A.phase_dbg[((size_t)b * 2 + 1) * T + t0 + k] = p2lo(arg2);
+          }
+          if ((t0 + k + 1) < T) {
+            A.phase_dbg[((size_t)b * 2 + 0) * T + t0 + k + 1] = p2hi(arg1);
+            A.phase_dbg[((size_t)b * 2 + 1) * T + t0 + k + 1] = p2hi(arg2);
           }
         }
       }
@@ -687,6 +832,7 @@ int launch_audio(const AudioArgs& a, const VoiceWorkspace& w, bool dbg, cudaStre
   IAS_SHAPE(128, 16, 3)
   IAS_SHAPE(256, 8, 3)
   IAS_SHAPE(256, 16, 2)
+  IAS_SHAPE(128, 16, 5)
   IAS_SHAPE(128, 12, 5)
   IAS_SHAPE(96, 16, 5)
   IAS_SHAPE(64, 16, 8)
