@@ -136,6 +136,7 @@ struct ControlShared {
   ModMatrix mm;
   double wsum[2][CTRL_THREADS / 32];
   int last_nz[CTRL_THREADS / 32];
+  float range[CTRL_THREADS / 32][4];
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -264,6 +265,7 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
   const float lev3 = sh.P[MIX + 2];
   float4* rv = rec + (size_t)b * C * (REC_FLOATS / 4);
   int last_nz = -1;  // last control point where any amplitude signal (vco_1_amp, vco_2_amp, noise_amp) is non-zero
+  float lo1 = 1e30f, hi1 = -1e30f, lo2 = 1e30f, hi2 = -1e30f;  // range of the two pitch signals
   for (int j = tid; j < C; j += CTRL_THREADS) {
     const int ja = min(j + 1, C - 1), jb = min(j + 2, C - 1);
     const float* s0 = src + 0 * C;
@@ -279,17 +281,47 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
     rv[j * 4 + 2] = make_float4(g1.dd, g2.c0, g2.d0, g2.dd);
     rv[j * 4 + 3] = make_float4(g3.c0, g3.d0, g3.dd, 0.0f);
     if (s1[j] != 0.0f || s3[j] != 0.0f || s4[j] != 0.0f) last_nz = j;
+    lo1 = fminf(lo1, s0[j]);
+    hi1 = fmaxf(hi1, s0[j]);
+    lo2 = fminf(lo2, s2[j]);
+    hi2 = fmaxf(hi2, s2[j]);
   }
   // Envelopes end in exact zeros (pow(0, alpha) == 0 after the release): tell the audio stage where the silent tail
   // starts so it can write zeros instead of rendering oscillators that are multiplied by 0.
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) last_nz = max(last_nz, __shfl_xor_sync(0xffffffffu, last_nz, d));
-  if (lane == 0) sh.last_nz[warp] = last_nz;
+  for (int d = 16; d > 0; d >>= 1) {
+    last_nz = max(last_nz, __shfl_xor_sync(0xffffffffu, last_nz, d));
+    lo1 = fminf(lo1, __shfl_xor_sync(0xffffffffu, lo1, d));
+    hi1 = fmaxf(hi1, __shfl_xor_sync(0xffffffffu, hi1, d));
+    lo2 = fminf(lo2, __shfl_xor_sync(0xffffffffu, lo2, d));
+    hi2 = fmaxf(hi2, __shfl_xor_sync(0xffffffffu, hi2, d));
+  }
+  if (lane == 0) {
+    sh.last_nz[warp] = last_nz;
+    sh.range[warp][0] = lo1;
+    sh.range[warp][1] = hi1;
+    sh.range[warp][2] = lo2;
+    sh.range[warp][3] = hi2;
+  }
   __syncthreads();
   if (tid == 0) {
     int m = -1;
-    for (int w = 0; w < CTRL_THREADS / 32; ++w) m = max(m, sh.last_nz[w]);
+    for (int w = 0; w < CTRL_THREADS / 32; ++w) {
+      m = max(m, sh.last_nz[w]);
+      lo1 = fminf(lo1, sh.range[w][0]);
+      hi1 = fmaxf(hi1, sh.range[w][1]);
+      lo2 = fminf(lo2, sh.range[w][2]);
+      hi2 = fmaxf(hi2, sh.range[w][3]);
+    }
     vconst[(size_t)b * VC_COUNT + VC_SILENT_FROM] = (float)(m + 1);
+    // Interpolated values stay within the range of the control points (up to an ulp), so with a 0.5-semitone margin
+    // clamp(midi + depth*mod, 0, 127) provably never engages.  NaNs fail the comparisons and keep the clamp.
+    const float midi1 = add(sh.P[KEY_MIDI_F0], sh.P[VCO1 + 0]), d1 = sh.P[VCO1 + 1];
+    const float midi2 = add(sh.P[KEY_MIDI_F0], sh.P[VCO2 + 0]), d2 = sh.P[VCO2 + 1];
+    const float a1 = midi1 + fminf(d1 * lo1, d1 * hi1), b1 = midi1 + fmaxf(d1 * lo1, d1 * hi1);
+    const float a2 = midi2 + fminf(d2 * lo2, d2 * hi2), b2 = midi2 + fmaxf(d2 * lo2, d2 * hi2);
+    const bool inside = a1 > 0.5f && b1 < 126.5f && a2 > 0.5f && b2 < 126.5f;
+    vconst[(size_t)b * VC_COUNT + VC_NOCLAMP] = inside ? 1.0f : 0.0f;
   }
 }
 
@@ -417,11 +449,15 @@ __device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
 }
 
 // vm::vco_increment for two samples: 2*pi*hz(clamp(midi + depth*mod, 0, 127)) / sample_rate, same op order.
+template <bool CLAMP>
 __device__ __forceinline__ P2 vco_increment_p2(float midi, float depth, P2 mod, float sr, float rsr) {
   const P2 dm = p2_mul(p2b(depth), mod);
   // scalar adds: the product keeps its own rounding (see the note on contraction above)
-  const float m0 = fminf(fmaxf(add(midi, p2lo(dm)), 0.0f), 127.0f);
-  const float m1 = fminf(fmaxf(add(midi, p2hi(dm)), 0.0f), 127.0f);
+  float m0 = add(midi, p2lo(dm)), m1 = add(midi, p2hi(dm));
+  if (CLAMP) {  // voices whose range is provably inside (VC_NOCLAMP) skip the four min/max instructions
+    m0 = fminf(fmaxf(m0, 0.0f), 127.0f);
+    m1 = fminf(fmaxf(m1, 0.0f), 127.0f);
+  }
   const P2 a = p2_add(p2(m0, m1), p2b(-69.0f));
   // a / 12: Markstein step with RN(1/12)  (div_const)
   const P2 q = p2_mul(a, p2b(0.0833333358168601989746f));
@@ -461,10 +497,16 @@ __device__ __forceinline__ P2 cospi_p2(P2 f, P2 t) {
   const P2 fr = p2_mul(f, p2b(IAS_PI_F));
   return p2(flip_sign(__cosf(p2lo(fr)), p2lo(t)), flip_sign(__cosf(p2hi(fr)), p2hi(t)));
 }
+// cos(a) for the sine VCO: reduce to full turns, f in [-0.5, 0.5] (same FMA scheme as reduce_half_turns with 1/(2 pi)),
+// so the SFU cosine needs no sign fix-up afterwards.  Amplitude path: absolute error ~5e-7.
 __device__ __forceinline__ P2 cos_arg_p2(P2 a) {
-  P2 f, t;
-  reduce_half_turns_p2(a, f, t);
-  return cospi_p2(f, t);
+  const float C1 = 0.159154936671257019f;                                              // (float)(1/(2 pi))
+  const float C2 = (float)(0.15915494309189533577 - (double)0.159154936671257019f);    // 1/(2 pi) - C1
+  const float magic = 12582912.0f;
+  const P2 t = p2_fma(a, p2b(C1), p2b(magic));
+  const P2 nneg = p2_sub(p2b(magic), t);
+  const P2 fr = p2_mul(p2_fma(a, p2b(C2), p2_fma(a, p2b(C1), nneg)), p2b(IAS_TWO_PI_F));
+  return p2(__cosf(p2lo(fr)), __cosf(p2hi(fr)));
 }
 // vm::squaresaw_core for two arguments
 __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
@@ -486,6 +528,37 @@ __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p2hi(ep)));
   const P2 th = p2_fma(p2b(-2.0f), p2(r0, r1), p2b(1.0f));
   return p2_mul(th, p2_fma(p2b(shape), cospi_p2(f, t), p2b(1.0f)));
+}
+
+// Pass 1 of a tile for one thread: the phase increments of both VCOs for its SPT samples (two samples per packed
+// instruction), bit for bit the reference's fp32 op sequence.  srcs[] keeps the fp32 source coordinates for pass 2.
+template <int SPT, bool VEC, bool CLAMP>
+__device__ __forceinline__ void pitch_pass(float (&x1)[SPT], float (&x2)[SPT], float (&srcs)[SPT], const float4 r0,
+                                           const float4 r1, float ft0, float scale, float fj, float fj1, float midi1,
+                                           float depth1, float midi2, float depth2, float sr, float rsr, int t0, int T) {
+#pragma unroll
+  for (int k = 0; k < SPT; k += 2) {
+    const P2 fi = p2_add(p2b(ft0), p2((float)k, (float)(k + 1)));
+    // the reference's fp32 source coordinate; scalar products so that they are rounded before the subtraction
+    const float s0 = mul(scale, p2lo(fi)), s1 = mul(scale, p2hi(fi));
+    srcs[k] = s0;
+    srcs[k + 1] = s1;
+    const bool d0 = s0 >= fj1, d1 = s1 >= fj1;
+    const P2 l1 = p2_sub(p2(s0, s1), p2(d0 ? fj1 : fj, d1 ? fj1 : fj));  // in [0,1): j = floor(src) of sample 0
+    const P2 l0 = p2_sub(p2b(1.0f), l1);
+    // upsample_mix: fma(l0, x[i0], l1 * x[i1])
+    const P2 m1 = p2_fma(l0, p2(d0 ? r0.y : r0.x, d1 ? r0.y : r0.x), p2_mul(l1, p2(d0 ? r0.z : r0.y, d1 ? r0.z : r0.y)));
+    const P2 m2 = p2_fma(l0, p2(d0 ? r1.x : r0.w, d1 ? r1.x : r0.w), p2_mul(l1, p2(d0 ? r1.y : r1.x, d1 ? r1.y : r1.x)));
+    const P2 i1 = vco_increment_p2<CLAMP>(midi1, depth1, m1, sr, rsr);
+    const P2 i2 = vco_increment_p2<CLAMP>(midi2, depth2, m2, sr, rsr);
+    // VEC: T % SPT == 0, so a thread is wholly live or wholly past the end; dead threads sit after every live
+    // one in the last tile, and an inclusive scan never feeds later totals into earlier lanes -> no masking.
+    const bool live0 = VEC || (t0 + k) < T, live1 = VEC || (t0 + k + 1) < T;
+    x1[k] = live0 ? p2lo(i1) : 0.0f;
+    x1[k + 1] = live1 ? p2hi(i1) : 0.0f;
+    x2[k] = live0 ? p2lo(i2) : 0.0f;
+    x2[k + 1] = live1 ? p2hi(i2) : 0.0f;
+  }
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -516,6 +589,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
     const float midi1 = vc[VC_MIDI1], depth1 = vc[VC_DEPTH1], phase1 = vc[VC_PHASE1];
     const float midi2 = vc[VC_MIDI2], depth2 = vc[VC_DEPTH2], phase2 = vc[VC_PHASE2];
     const float pk = vc[VC_PK], shape = vc[VC_SHAPE];
+    const bool noclamp = vc[VC_NOCLAMP] != 0.0f;
     const float4* rec = A.rec + (size_t)b * C * (REC_FLOATS / 4);
     const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
     float* out = A.audio + (size_t)b * T;
@@ -543,31 +617,12 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
       float x1[SPT], x2[SPT], srcs[SPT];
       const float4 r0 = __ldg(rj + 0);
       const float4 r1 = __ldg(rj + 1);
-#pragma unroll
-      for (int k = 0; k < SPT; k += 2) {  // two samples per packed instruction
-        const P2 fi = p2_add(p2b(ft0), p2((float)k, (float)(k + 1)));
-        // the reference's fp32 source coordinate; scalar products so that they are rounded before the subtraction
-        const float s0 = mul(scale, p2lo(fi)), s1 = mul(scale, p2hi(fi));
-        srcs[k] = s0;
-        srcs[k + 1] = s1;
-        const bool d0 = s0 >= fj1, d1 = s1 >= fj1;
-        const P2 l1 = p2_sub(p2(s0, s1), p2(d0 ? fj1 : fj, d1 ? fj1 : fj));  // in [0,1): j = floor(src) of sample 0
-        const P2 l0 = p2_sub(p2b(1.0f), l1);
-        // upsample_mix: fma(l0, x[i0], l1 * x[i1])
-        const P2 m1 = p2_fma(l0, p2(d0 ? r0.y : r0.x, d1 ? r0.y : r0.x),
-                             p2_mul(l1, p2(d0 ? r0.z : r0.y, d1 ? r0.z : r0.y)));
-        const P2 m2 = p2_fma(l0, p2(d0 ? r1.x : r0.w, d1 ? r1.x : r0.w),
-                             p2_mul(l1, p2(d0 ? r1.y : r1.x, d1 ? r1.y : r1.x)));
-        const P2 i1 = vco_increment_p2(midi1, depth1, m1, A.sr, A.rsr);
-        const P2 i2 = vco_increment_p2(midi2, depth2, m2, A.sr, A.rsr);
-        // VEC: T % SPT == 0, so a thread is wholly live or wholly past the end; dead threads sit after every live
-        // one in the last tile, and an inclusive scan never feeds later totals into earlier lanes -> no masking.
-        const bool live0 = VEC || (t0 + k) < T, live1 = VEC || (t0 + k + 1) < T;
-        x1[k] = live0 ? p2lo(i1) : 0.0f;
-        x1[k + 1] = live1 ? p2hi(i1) : 0.0f;
-        x2[k] = live0 ? p2lo(i2) : 0.0f;
-        x2[k + 1] = live1 ? p2hi(i2) : 0.0f;
-      }
+      if (noclamp)
+        pitch_pass<SPT, VEC, false>(x1, x2, srcs, r0, r1, ft0, scale, fj, fj1, midi1, depth1, midi2, depth2, A.sr, A.rsr,
+                                    t0, T);
+      else
+        pitch_pass<SPT, VEC, true>(x1, x2, srcs, r0, r1, ft0, scale, fj, fj1, midi1, depth1, midi2, depth2, A.sr, A.rsr,
+                                   t0, T);
       // ---- block scan -------------------------------------------------------------------------------------
       double tot1 = 0.0, tot2 = 0.0;
 #pragma unroll

@@ -498,6 +498,8 @@ enum VoiceConst {
   VC_SHAPE, VC_GAIN2,  // shape, 1 - shape/2
   VC_LEVEL1, VC_LEVEL2, VC_LEVEL3,
   VC_SILENT_FROM,  // control index from which all three amplitude signals are exactly 0 to the end (as float)
+  VC_NOCLAMP,      // 1.0 if midi + depth*mod stays inside (0.5, 126.5) for both VCOs over the whole clip: the clamp
+                   // to [0, 127] is then the identity and the audio stage skips it
   VC_COUNT = 16
 };
 
