@@ -73,31 +73,38 @@ struct SeedTable {
   uint8_t frozen[NROWS];
 };
 
-__global__ void __launch_bounds__(128) k_seed_params(long long first_id, const long long* __restrict__ batch_idx_dev,
-                                                     int B, SeedTable tab, float* __restrict__ params01,
-                                                     uint8_t* __restrict__ is_train) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
+constexpr int SEED_THREADS = 64;
+
+__global__ void __launch_bounds__(SEED_THREADS) k_seed_params(long long first_id,
+                                                              const long long* __restrict__ batch_idx_dev, int B,
+                                                              SeedTable tab, float* __restrict__ params01,
+                                                              uint8_t* __restrict__ is_train) {
+  // MT19937 state words mt[0..78] of this CTA's sounds, [word][thread]: conflict-free, and no per-thread local array
+  __shared__ uint32_t s_lo[NROWS + 1][SEED_THREADS];
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * SEED_THREADS + tid;
+  if (i >= B) return;  // no barrier below: every thread only touches its own column
   if (batch_idx_dev) first_id = *batch_idx_dev * (long long)B;  // batch number read on the device (graph replay)
-  unsigned long long id = (unsigned long long)(first_id + i);
-  // MT19937 state after init_genrand(low 32 bits of the seed); only mt[0..78] and mt[397..474] feed outputs 0..77
-  uint32_t lo[NROWS + 1];
-  uint32_t hi[NROWS];
+  const unsigned long long id = (unsigned long long)(first_id + i);
+  // init_genrand(low 32 bits of the seed); only mt[0..78] and mt[397..474] feed outputs 0..77
   uint32_t s = (uint32_t)id;
-  lo[0] = s;
-  for (int j = 1; j <= 396 + NROWS; ++j) {
+  s_lo[0][tid] = s;
+#pragma unroll 6
+  for (int j = 1; j <= NROWS; ++j) {
     s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)j;
-    if (j <= NROWS) lo[j] = s;
-    if (j >= 397) hi[j - 397] = s;
+    s_lo[j][tid] = s;
   }
+#pragma unroll 6
+  for (int j = NROWS + 1; j < 397; ++j) s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)j;
   for (int k = 0; k < NROWS; ++k) {
-    uint32_t y = (lo[k] & 0x80000000u) | (lo[k + 1] & 0x7fffffffu);
-    uint32_t v = hi[k] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(397 + k);  // mt[397 + k]
+    const uint32_t y = (s_lo[k][tid] & 0x80000000u) | (s_lo[k + 1][tid] & 0x7fffffffu);
+    uint32_t v = s ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
     v ^= v >> 11;
     v ^= (v << 7) & 0x9d2c5680u;
     v ^= (v << 15) & 0xefc60000u;
     v ^= v >> 18;
-    int row = tab.reg_of_sorted[k];
+    const int row = tab.reg_of_sorted[k];
     if (!tab.frozen[row]) params01[(size_t)row * B + i] = (float)(v & 0xffffffu) * (1.0f / 16777216.0f);
   }
   if (is_train) is_train[i] = ((id / 32ull) % 10ull) != 9ull;
@@ -924,7 +931,7 @@ int seed_params(int64_t first_sound_id, const int64_t* batch_idx_dev, int B, con
   }
   {
     ProfScope prof_(K_SEED_PARAMS, as_stream(stream));
-    k_seed_params<<<(B + 127) / 128, 128, 0, as_stream(stream)>>>(
+    k_seed_params<<<(B + SEED_THREADS - 1) / SEED_THREADS, SEED_THREADS, 0, as_stream(stream)>>>(
         (long long)first_sound_id, reinterpret_cast<const long long*>(batch_idx_dev), B, tab, params01, is_train);
   }
   IAS_LAUNCH_CHECK("k_seed_params");
