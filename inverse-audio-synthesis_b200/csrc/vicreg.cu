@@ -24,10 +24,12 @@ constexpr int TILE_FLOATS = TILE * KBLK;          // 4096 floats = 16 KiB per op
 constexpr int TILE_BYTES = TILE_FLOATS * 4;
 constexpr int STAGES = 3;
 constexpr int COLSUM_ROWS = 128;  // rows per k_colsum CTA
+constexpr int COV_ROWS = 4;       // Gram rows per k_cov_reduce CTA (128-column tile): 2 elements per thread
+constexpr int PACK_KB = 1;        // K-blocks (32 batch rows) per k_center_pack CTA: B/32 x 2 CTAs keep every SM busy
 constexpr int MAX_SPLITS = 64;
 
 struct Plan {
-  int B, D, DT, Dp, KB, ntiles, splits, P, MT;
+  int B, D, DT, Dp, KB, ntiles, splits, P, MT, NV;
   size_t off_partial, off_varpart, off_repr, off_mean, off_packed, off_gram, off_covp, off_diag, off_stats, off_gfull, off_rowpack, off_gpack, total;
 };
 
@@ -53,12 +55,13 @@ __host__ inline Plan make_plan(int B, int D) {
     return r;
   };
   p.off_partial = take((size_t)p.P * 2 * D);
-  p.off_varpart = take((size_t)p.P * 2 * D);
+  p.NV = (p.KB + PACK_KB - 1) / PACK_KB;  // k_center_pack CTAs per side = centred second-moment partials
+  p.off_varpart = take((size_t)p.NV * 2 * D);
   p.off_repr = take((size_t)p.P);
   p.off_mean = take((size_t)2 * D);
   p.off_packed = take((size_t)2 * 2 * p.DT * p.KB * TILE_FLOATS);
   p.off_gram = take((size_t)2 * p.ntiles * p.splits * TILE * TILE);
-  p.off_covp = take((size_t)2 * p.ntiles * TILE);
+  p.off_covp = take((size_t)2 * p.ntiles * (TILE / COV_ROWS));
   p.off_diag = take((size_t)2 * p.Dp);
   p.off_stats = take((size_t)8 * p.Dp);
   p.MT = (B + TILE - 1) / TILE;
@@ -212,7 +215,6 @@ __device__ __forceinline__ float to_tf32(float v) {
   return __uint_as_float(r);
 }
 
-constexpr int PACK_KB = COLSUM_ROWS / KBLK;  // K-blocks per k_center_pack CTA (same row blocking as k_colsum)
 
 __global__ void __launch_bounds__(256) k_center_pack(const float* __restrict__ x, const float* __restrict__ y, int B,
                                                      int D, int P, int DT, int KB, const float* __restrict__ partial,
@@ -258,7 +260,12 @@ __global__ void __launch_bounds__(256) k_center_pack(const float* __restrict__ x
     }
     // centred second moment of this CTA's 128 rows (fp32, two-level); the variance comes from these, not from the
     // Gram diagonal: the hinge 1 - std amplifies a relative error of the variance by ~1/(1 - std)
-    if (d < D) varpart[((size_t)pb * 2 + s) * D + d] = (sq4[0] + sq4[1]) + (sq4[2] + sq4[3]);
+    if (d < D) {
+      float sq = 0.0f;
+#pragma unroll
+      for (int q = 0; q < PACK_KB; ++q) sq += sq4[q];
+      varpart[((size_t)pb * 2 + s) * D + d] = sq;
+    }
   }
 }
 
@@ -636,8 +643,8 @@ __global__ void __launch_bounds__(256) k_cov_reduce(const float* __restrict__ gr
                                                     float* __restrict__ diag_out, float* __restrict__ gram_full) {
   __shared__ float s_red[8];
   int u = blockIdx.x;
-  const int rb = u % (TILE / 16);
-  u /= (TILE / 16);
+  const int rb = u % (TILE / COV_ROWS);
+  u /= (TILE / COV_ROWS);
   const int t = u % ntiles;
   const int s = u / ntiles;
   int tm = 0, rem = t;
@@ -648,8 +655,8 @@ __global__ void __launch_bounds__(256) k_cov_reduce(const float* __restrict__ gr
   const int tn = tm + rem;
   const float* base = gram_partial + (((size_t)s * ntiles + t) * splits) * TILE * TILE;
   float sq = 0.0f;
-  for (int e = threadIdx.x; e < 16 * TILE; e += 256) {
-    const int r = rb * 16 + e / TILE, c = e % TILE;
+  for (int e = threadIdx.x; e < COV_ROWS * TILE; e += 256) {
+    const int r = rb * COV_ROWS + e / TILE, c = e % TILE;
     float g = 0.0f;
     for (int k = 0; k < splits; ++k) g += base[(size_t)k * TILE * TILE + (size_t)r * TILE + c];
     const int gi = tm * TILE + r, gj = tn * TILE + c;
@@ -680,10 +687,10 @@ __global__ void __launch_bounds__(256) k_cov_reduce(const float* __restrict__ gr
 struct FinalArgs {
   const float* repr;   // [P]
   const float* covp;   // [2 * ntiles * 8]
-  const float* varpart;  // [P][2][D] centred second-moment partials
+  const float* varpart;  // [NV][2][D] centred second-moment partials
   float* stats;        // [2][Dp] std
   float* out4;
-  int P, ncovp_per_side, D, Dp, B, B_local, cfgB, embeddim;
+  int P, NV, ncovp_per_side, D, Dp, B, B_local, cfgB, embeddim;
   float sim, stdc, covc;
 };
 
@@ -692,8 +699,15 @@ __global__ void __launch_bounds__(256) k_finalize(FinalArgs a) {
   for (int d = threadIdx.x; d < a.D; d += 256) {
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      float ss = 0.0f;
-      for (int p = 0; p < a.P; ++p) ss += a.varpart[((size_t)p * 2 + s) * a.D + d];
+      // NV partials (one per 32 batch rows): four independent accumulators keep the loads in flight
+      float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      int p = 0;
+      for (; p + 4 <= a.NV; p += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s4[q] += a.varpart[((size_t)(p + q) * 2 + s) * a.D + d];
+      }
+      for (; p < a.NV; ++p) s4[0] += a.varpart[((size_t)p * 2 + s) * a.D + d];
+      const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       const float var = ss / (float)(a.B - 1);  // NaN for B == 1, as torch.var
       const float sd = sqrtf(var + 0.0001f);
       a.stats[s * a.Dp + d] = sd;
@@ -788,7 +802,7 @@ int run_stats_and_gram(const RowSrc& src, const float* x, const float* y, float*
   IAS_LAUNCH_CHECK("k_colsum");
   {
     ProfScope prof_(K_VICREG_PACK, st);
-    k_center_pack<<<dim3(p.P, 2), 256, 0, st>>>(x, y, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
+    k_center_pack<<<dim3(p.NV, 2), 256, 0, st>>>(x, y, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
                                                 w + p.off_varpart, w + p.off_packed);
   }
   IAS_LAUNCH_CHECK("k_center_pack");
@@ -796,7 +810,7 @@ int run_stats_and_gram(const RowSrc& src, const float* x, const float* y, float*
   if (rc) return rc;
   {
     ProfScope prof_(K_VICREG_COV_REDUCE, st);
-    k_cov_reduce<<<2 * p.ntiles * (TILE / 16), 256, 0, st>>>(w + p.off_gram, p.DT, p.ntiles, p.splits, p.Dp,
+    k_cov_reduce<<<2 * p.ntiles * (TILE / COV_ROWS), 256, 0, st>>>(w + p.off_gram, p.DT, p.ntiles, p.splits, p.Dp,
                                                              w + p.off_covp, w + p.off_diag, gram_full);
   }
   IAS_LAUNCH_CHECK("k_cov_reduce");
@@ -835,7 +849,8 @@ extern "C" int ias_vicreg_loss(const float* x, const float* y, int B, int local_
   a.stats = w + p.off_stats;
   a.out4 = out4;
   a.P = p.P;
-  a.ncovp_per_side = p.ntiles * (TILE / 16);
+  a.NV = p.NV;
+  a.ncovp_per_side = p.ntiles * (TILE / COV_ROWS);
   a.D = D; a.Dp = p.Dp; a.B = B; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
   a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
   {
@@ -869,7 +884,7 @@ extern "C" int ias_vicreg_gram_reference(const float* x, int B, int D, float* gr
   cudaStream_t st = as_stream(stream);
   k_colsum<<<p.P, 256, 0, st>>>(single_src(x, x, B), p.B, p.D, 0, B, w + p.off_partial, w + p.off_repr, nullptr, nullptr);
   IAS_LAUNCH_CHECK("k_colsum");
-  k_center_pack<<<dim3(p.P, 2), 256, 0, st>>>(x, x, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
+  k_center_pack<<<dim3(p.NV, 2), 256, 0, st>>>(x, x, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
                                               w + p.off_varpart, w + p.off_packed);
   IAS_LAUNCH_CHECK("k_center_pack");
   {
@@ -994,7 +1009,8 @@ extern "C" int ias_vicreg_loss_gather(const float* const* x_peers_host, const fl
   a.stats = w + p.off_stats;
   a.out4 = out4;
   a.P = p.P;
-  a.ncovp_per_side = p.ntiles * (TILE / 16);
+  a.NV = p.NV;
+  a.ncovp_per_side = p.ntiles * (TILE / COV_ROWS);
   a.D = D; a.Dp = p.Dp; a.B = p.B; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
   a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
   {
