@@ -132,8 +132,10 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
 // k_voice_control
 // ------------------------------------------------------------------------------------------------------------
 constexpr int CTRL_THREADS = 256;
+// CTAs per SM of the control kernel: 4 (64 registers, 40 B of spills) turn 1024 voices into 2 rounds of 592 instead
+// of 3 rounds of 444.
 #ifndef IAS_CTRL_MINB
-#define IAS_CTRL_MINB 2
+#define IAS_CTRL_MINB 4
 #endif
 constexpr int REC_FLOATS = 16;  // floats per control-interval record (4 x 16-byte loads in the audio stage)
 
@@ -214,9 +216,27 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
   float* out = SMEM ? s_rows + 2 * C : ctrl_ws + (size_t)b * IAS_VOICE_NCONTROL * C;
   // Phase A: LFO phase increments from the rate envelopes
   const float rcr = rcp(cr);
-  for (int j = tid; j < C; j += CTRL_THREADS) {
-    ph0[j] = lfo_increment(sh.lfo[0], env[4 * C + j], cr, rcr);
-    ph1[j] = lfo_increment(sh.lfo[1], env[5 * C + j], cr, rcr);
+  constexpr int UJ = 4;  // control points per thread in flight: the envelope loads of all of them are issued first
+  for (int jb = tid; jb < C; jb += UJ * CTRL_THREADS) {
+    float e4[UJ], e5[UJ];
+#pragma unroll
+    for (int u = 0; u < UJ; ++u) {
+      const int j = jb + u * CTRL_THREADS;
+      if (j < C) {
+        // (the read-only path only when the rows are not rewritten in place by this kernel)
+        e4[u] = SMEM ? __ldg(env + 4 * C + j) : env[4 * C + j];
+        e5[u] = SMEM ? __ldg(env + 5 * C + j) : env[5 * C + j];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UJ; ++u) {
+      const int j = jb + u * CTRL_THREADS;
+      if (j < C) {
+        const float i0 = lfo_increment(sh.lfo[0], e4[u], cr, rcr), i1 = lfo_increment(sh.lfo[1], e5[u], cr, rcr);
+        ph0[j] = i0;
+        ph1[j] = i1;
+      }
+    }
   }
   __syncthreads();
 
@@ -251,15 +271,31 @@ k_voice_control(const float* __restrict__ params01, int B, int C, float cr, floa
 
   // Phase C: LFO shapes, VCAs, modulation matrix
   float* user = ctrl_out ? ctrl_out + (size_t)b * IAS_VOICE_NCONTROL * C : nullptr;
-  for (int j = tid; j < C; j += CTRL_THREADS) {
-    float l1 = mul(lfo_shapes_mix(sh.lfo[0], ph0[j]), env[2 * C + j]);
-    float l2 = mul(lfo_shapes_mix(sh.lfo[1], ph1[j]), env[3 * C + j]);
-    float a1 = env[0 * C + j], a2 = env[1 * C + j];
+  for (int jb = tid; jb < C; jb += UJ * CTRL_THREADS) {
+    float e0[UJ], e1[UJ], e2[UJ], e3[UJ];
 #pragma unroll
-    for (int o = 0; o < 5; ++o) {
-      const float v = modmatrix_out(sh.mm, o, a1, a2, l1, l2);
-      out[o * C + j] = v;
-      if (user) user[o * C + j] = v;
+    for (int u = 0; u < UJ; ++u) {
+      const int j = jb + u * CTRL_THREADS;
+      if (j < C) {
+        e0[u] = SMEM ? __ldg(env + 0 * C + j) : env[0 * C + j];
+        e1[u] = SMEM ? __ldg(env + 1 * C + j) : env[1 * C + j];
+        e2[u] = SMEM ? __ldg(env + 2 * C + j) : env[2 * C + j];
+        e3[u] = SMEM ? __ldg(env + 3 * C + j) : env[3 * C + j];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UJ; ++u) {
+      const int j = jb + u * CTRL_THREADS;
+      if (j < C) {
+        const float l1 = mul(lfo_shapes_mix(sh.lfo[0], ph0[j]), e2[u]);
+        const float l2 = mul(lfo_shapes_mix(sh.lfo[1], ph1[j]), e3[u]);
+#pragma unroll
+        for (int o = 0; o < 5; ++o) {
+          const float v = modmatrix_out(sh.mm, o, e0[u], e1[u], l1, l2);
+          out[o * C + j] = v;
+          if (user) user[o * C + j] = v;
+        }
+      }
     }
   }
   __syncthreads();  // this CTA's output rows are re-read below
@@ -818,7 +854,7 @@ int launch_control(const float* params01, int B, int C, float cr, float eps, con
     // 4 s clips: phase + output rows in shared memory (7*C floats); longer clips fall back to global scratch rows
     const size_t smem = (size_t)7 * C * sizeof(float);
     static bool attr_set = false;
-    constexpr size_t SMEM_LIMIT = 100 * 1024;  // two CTAs per SM
+    constexpr size_t SMEM_LIMIT = 56 * 1024;  // four CTAs per SM
     if (!attr_set) {
       IAS_CUDA(cudaFuncSetAttribute(k_voice_control<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
       attr_set = true;
