@@ -463,11 +463,13 @@ __device__ __forceinline__ P2 p2b(float a) { return p2(a, a); }  // broadcast (a
 __device__ __forceinline__ float p2lo(P2 a) {
   float x, y;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  (void)y;
   return x;
 }
 __device__ __forceinline__ float p2hi(P2 a) {
   float x, y;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  (void)x;
   return y;
 }
 __device__ __forceinline__ P2 p2_fma(P2 a, P2 b, P2 c) {
