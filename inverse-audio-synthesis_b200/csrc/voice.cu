@@ -460,6 +460,7 @@ __device__ __forceinline__ P2 p2(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ P2 p2b(float a) { return p2(a, a); }  // broadcast (a scalar / immediate operand in SASS)
+#pragma nv_diag_suppress 550  // the unused half of an unpacked pair
 __device__ __forceinline__ float p2lo(P2 a) {
   float x, y;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
@@ -472,6 +473,7 @@ __device__ __forceinline__ float p2hi(P2 a) {
   (void)x;
   return y;
 }
+#pragma nv_diag_default 550
 __device__ __forceinline__ P2 p2_fma(P2 a, P2 b, P2 c) {
   P2 r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
