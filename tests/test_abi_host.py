@@ -58,6 +58,26 @@ def test_library_loads_and_reports_errors(built_lib):
     assert lib.ias_vicreg_workspace_bytes(8192, 256) > 2 * 2 * 8192 * 256 * 4
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu(built_lib):
+    """ias_voice_seed_params_dev / ias_pqmf_analysis_image reject bad arguments before touching CUDA; the Python
+    surfaces refuse CPU tensors (no fallback)."""
+    import ias_b200
+
+    lib = ias_b200.lib()
+    assert lib.ias_voice_seed_params_dev(None, 32, None, None, None, None) == 1
+    assert b"batch_idx_dev" in lib.ias_last_error()
+    rc = lib.ias_pqmf_analysis_image(None, None, None, None, None, None, None, None, None, None, 4, 100, 3, 63, None)
+    assert rc == 1 and b"mean/std" in lib.ias_last_error()
+    gram = ias_b200.PQMF(N=3)
+    with pytest.raises(ias_b200.IasError):
+        gram.analysis_image(torch.zeros(2, 1, 1000), [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    with pytest.raises(ValueError):
+        gram.analysis_image(torch.zeros(2, 1, 1000), [0.5], [0.5])
+    voice = ias_b200.Voice(synthconfig=ias_b200.SynthConfig(batch_size=32, reproducible=True, buffer_size_seconds=0.1))
+    with pytest.raises(ias_b200.IasError):
+        voice(0)  # parameters live on the CPU until .to(device): no CPU render path exists
+
+
 def test_voice_tables_match_oracle(built_lib):
     import ias_b200
 
