@@ -694,50 +694,62 @@ struct FinalArgs {
   float sim, stdc, covc;
 };
 
-__global__ void __launch_bounds__(256) k_finalize(FinalArgs a) {
+constexpr int FIN_THREADS = 1024;
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize(FinalArgs a) {
+  // variance: NV partials (one per 32 batch rows) per dimension and side; four threads share a dimension so that the
+  // 2*NV*D loads of a large gathered batch (NV = 256 at B = 8192) are spread over the whole CTA
+  __shared__ float s_var[4][256];
+  const int t = threadIdx.x, col = t & 255, part = t >> 8;
   float hinge[2] = {0.0f, 0.0f};
-  for (int d = threadIdx.x; d < a.D; d += 256) {
+  for (int d0 = 0; d0 < a.D; d0 += 256) {
+    const int d = d0 + col;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      // NV partials (one per 32 batch rows): four independent accumulators keep the loads in flight
-      float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      int p = 0;
-      for (; p + 4 <= a.NV; p += 4) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s4[q] += a.varpart[((size_t)(p + q) * 2 + s) * a.D + d];
+      float acc0 = 0.0f, acc1 = 0.0f;
+      if (d < a.D) {
+        int p = part;
+        for (; p + 4 < a.NV; p += 8) {
+          acc0 += a.varpart[((size_t)p * 2 + s) * a.D + d];
+          acc1 += a.varpart[((size_t)(p + 4) * 2 + s) * a.D + d];
+        }
+        if (p < a.NV) acc0 += a.varpart[((size_t)p * 2 + s) * a.D + d];
       }
-      for (; p < a.NV; ++p) s4[0] += a.varpart[((size_t)p * 2 + s) * a.D + d];
-      const float ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      const float var = ss / (float)(a.B - 1);  // NaN for B == 1, as torch.var
-      const float sd = sqrtf(var + 0.0001f);
-      a.stats[s * a.Dp + d] = sd;
-      hinge[s] += fmaxf(1.0f - sd, 0.0f);
+      s_var[part][col] = acc0 + acc1;
+      __syncthreads();
+      if (part == 0 && d < a.D) {
+        const float ss = (s_var[0][col] + s_var[1][col]) + (s_var[2][col] + s_var[3][col]);
+        const float var = ss / (float)(a.B - 1);  // NaN for B == 1, as torch.var
+        const float sd = sqrtf(var + 0.0001f);
+        a.stats[s * a.Dp + d] = sd;
+        hinge[s] += fmaxf(1.0f - sd, 0.0f);
+      }
+      __syncthreads();
     }
   }
   // cov_x and cov_y partials are summed separately, then divided by embeddim, then added (vicreg.py:49-51)
   float covx = 0.0f, covy = 0.0f;
-  for (int i = threadIdx.x; i < a.ncovp_per_side; i += 256) {
+  for (int i = t; i < a.ncovp_per_side; i += FIN_THREADS) {
     covx += a.covp[i];
     covy += a.covp[a.ncovp_per_side + i];
   }
   float rp = 0.0f;
-  for (int i = threadIdx.x; i < a.P; i += 256) rp += a.repr[i];
+  for (int i = t; i < a.P; i += FIN_THREADS) rp += a.repr[i];
   float v[5] = {hinge[0], hinge[1], covx, covy, rp};
-  __shared__ float s_all[5][8];
+  __shared__ float s_all[5][FIN_THREADS / 32];
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
-    float t = v[q];
+    float tt = v[q];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if ((threadIdx.x & 31) == 0) s_all[q][threadIdx.x >> 5] = t;
+    for (int o = 16; o > 0; o >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, o);
+    if ((t & 31) == 0) s_all[q][t >> 5] = tt;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot[5];
     for (int q = 0; q < 5; ++q) {
-      float t = 0.0f;
-      for (int w = 0; w < 8; ++w) t += s_all[q][w];
-      tot[q] = t;
+      float tt = 0.0f;
+      for (int w = 0; w < FIN_THREADS / 32; ++w) tt += s_all[q][w];
+      tot[q] = tt;
     }
     const float repr_loss = tot[4] / ((float)a.B_local * (float)a.D);
     const float std_loss = (tot[0] / (float)a.D) / 2.0f + (tot[1] / (float)a.D) / 2.0f;
@@ -855,7 +867,7 @@ extern "C" int ias_vicreg_loss(const float* x, const float* y, int B, int local_
   a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
   {
     ProfScope prof_(K_VICREG_FINALIZE, st);
-    k_finalize<<<1, 256, 0, st>>>(a);
+    k_finalize<<<1, FIN_THREADS, 0, st>>>(a);
   }
   IAS_LAUNCH_CHECK("k_finalize");
   return IAS_OK;
@@ -1015,7 +1027,7 @@ extern "C" int ias_vicreg_loss_gather(const float* const* x_peers_host, const fl
   a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
   {
     ProfScope prof_(K_VICREG_FINALIZE, st);
-    k_finalize<<<1, 256, 0, st>>>(a);
+    k_finalize<<<1, FIN_THREADS, 0, st>>>(a);
   }
   IAS_LAUNCH_CHECK("k_finalize");
   return IAS_OK;
