@@ -538,12 +538,6 @@ __device__ __forceinline__ void reduce_half_turns_p2(P2 a, P2& f, P2& t) {
   const P2 nneg = p2_sub(p2b(magic), t);  // -rint(a / pi)
   f = p2_fma(a, p2b(C2), p2_fma(a, p2b(C1), nneg));
 }
-__device__ __forceinline__ float flip_sign(float v, float t) { return i2f(f2i(v) ^ (f2i(t) << 31)); }
-// cos(pi * f) of both lanes through the SFU, sign flipped by the parity of n
-__device__ __forceinline__ P2 cospi_p2(P2 f, P2 t) {
-  const P2 fr = p2_mul(f, p2b(IAS_PI_F));
-  return p2(flip_sign(__cosf(p2lo(fr)), p2lo(t)), flip_sign(__cosf(p2hi(fr)), p2hi(t)));
-}
 // cos(a) for the sine VCO: reduce to full turns, f in [-0.5, 0.5] (same FMA scheme as reduce_half_turns with 1/(2 pi)),
 // so the SFU cosine needs no sign fix-up afterwards.  Amplitude path: absolute error ~5e-7.
 __device__ __forceinline__ P2 cos_arg_p2(P2 a) {
@@ -555,7 +549,10 @@ __device__ __forceinline__ P2 cos_arg_p2(P2 a) {
   const P2 fr = p2_mul(p2_fma(a, p2b(C2), p2_fma(a, p2b(C1), nneg)), p2b(IAS_TWO_PI_F));
   return p2(__cosf(p2lo(fr)), __cosf(p2hi(fr)));
 }
-// vm::squaresaw_core for two arguments
+// vm::squaresaw_core for two arguments: tanh(pk * sin(a)) * (1 + shape * cos(a)).  With a = (n + f) * pi and
+// sigma = (-1)^n: sin(a) = sigma * sin(pi f), cos(a) = sigma * cos(pi f), and tanh is odd, so the product equals
+// tanh(pk * sin(pi f)) * (sigma + shape * cos(pi f)) -- the parity enters once, as the float +-1 (one shift-add).
+__device__ __forceinline__ float parity_sign(float t) { return i2f((f2i(t) << 31) + 0x3f800000); }
 __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
   P2 f, t;
   reduce_half_turns_p2(a, f, t);
@@ -565,8 +562,7 @@ __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
   p = p2_fma(p, u, p2b(2.5499696731567383f));
   p = p2_fma(p, u, p2b(-5.1677045822143555f));
   p = p2_fma(p, u, p2b(3.141592502593994f));
-  const P2 sn = p2_mul(p, f);
-  const P2 sc = p2_mul(p2b(pk), p2(flip_sign(p2lo(sn), p2lo(t)), flip_sign(p2hi(sn), p2hi(t))));
+  const P2 sc = p2_mul(p2b(pk), p2_mul(p, f));  // pk * sin(pi f)
   float e0, e1, r0, r1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(p2lo(sc)));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(p2hi(sc)));
@@ -574,7 +570,9 @@ __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p2lo(ep)));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p2hi(ep)));
   const P2 th = p2_fma(p2b(-2.0f), p2(r0, r1), p2b(1.0f));
-  return p2_mul(th, p2_fma(p2b(shape), cospi_p2(f, t), p2b(1.0f)));
+  const P2 fr = p2_mul(f, p2b(IAS_PI_F));
+  const P2 c = p2(__cosf(p2lo(fr)), __cosf(p2hi(fr)));
+  return p2_mul(th, p2_fma(p2b(shape), c, p2(parity_sign(p2lo(t)), parity_sign(p2hi(t)))));
 }
 
 // Pass 1 of a tile for one thread: the phase increments of both VCOs for its SPT samples (two samples per packed
