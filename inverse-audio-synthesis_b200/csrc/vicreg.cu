@@ -130,12 +130,13 @@ __global__ void __launch_bounds__(256) k_colsum(RowSrc src, int B, int D, int lo
 // memory latency / 8 per row instead of one round trip per row.  Same outputs as k_colsum (the per-column sums add
 // the same values in a different order).
 constexpr int CS_CG = 64;                 // column quads per pass
-constexpr int CS_RG = 256 / CS_CG;        // row groups
-__global__ void __launch_bounds__(256) k_colsum_v4(RowSrc src, int B, int D, int local_row0, int local_rows,
+constexpr int CS_THREADS = 512;
+constexpr int CS_RG = CS_THREADS / CS_CG;  // row groups: 8 x 8 rows in flight = half of a CTA's 128 rows per round trip
+__global__ void __launch_bounds__(CS_THREADS) k_colsum_v4(RowSrc src, int B, int D, int local_row0, int local_rows,
                                                    float* __restrict__ partial, float* __restrict__ repr,
                                                    float* __restrict__ xg, float* __restrict__ yg) {
   __shared__ float4 s_part[2][CS_RG][CS_CG];
-  __shared__ float s_red[8];
+  __shared__ float s_red[CS_THREADS / 32];
   const int r0 = blockIdx.x * COLSUM_ROWS;
   const int r1 = min(r0 + COLSUM_ROWS, B);
   const int cg = threadIdx.x % CS_CG, rg = threadIdx.x / CS_CG;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(256) k_colsum_v4(RowSrc src, int B, int D, int
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.0f;
-    for (int w = 0; w < 8; ++w) t += s_red[w];
+    for (int w = 0; w < CS_THREADS / 32; ++w) t += s_red[w];
     repr[blockIdx.x] = t;
   }
 }
@@ -807,7 +808,7 @@ int run_stats_and_gram(const RowSrc& src, const float* x, const float* y, float*
     for (int q = 0; q < MAX_PEERS; ++q) v4 = v4 && ias_aligned16(src.x[q]) && ias_aligned16(src.y[q]);
     ProfScope prof_(K_VICREG_COLSUM, st);
     if (v4)
-      k_colsum_v4<<<p.P, 256, 0, st>>>(src, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr, xg, yg);
+      k_colsum_v4<<<p.P, CS_THREADS, 0, st>>>(src, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr, xg, yg);
     else
       k_colsum<<<p.P, 256, 0, st>>>(src, p.B, p.D, local_row0, B_local, w + p.off_partial, w + p.off_repr, xg, yg);
   }
