@@ -42,8 +42,9 @@ def bridge(bands: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torc
 
         flat = bands.contiguous().view(B, -1)
         feat = torch.empty((B, EMBED_DIM), dtype=torch.float32, device=bands.device)
-        _lib.check(_lib.lib().ias_abs_avg_pool(_lib.ptr(flat), _lib.ptr(feat), B, flat.shape[1], EMBED_DIM,
-                                               _lib.current_stream(bands.device)), "ias_abs_avg_pool")
+        with _lib.on_device(bands):
+            _lib.check(_lib.lib().ias_abs_avg_pool(_lib.ptr(flat), _lib.ptr(feat), B, flat.shape[1], EMBED_DIM,
+                                                   _lib.current_stream(bands.device)), "ias_abs_avg_pool")
     else:
         feat = torch.nn.functional.adaptive_avg_pool1d(bands.abs().reshape(B, 1, -1), EMBED_DIM).squeeze(1)
     return feat @ wa, params @ wp

@@ -53,3 +53,14 @@ struct ProfScope {
   } while (0)
 
 static inline bool ias_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Function attributes (opt-in shared memory) are per device: `seen` is a caller-owned bitmask of the devices already
+// configured.  Returns true the first time it is called for the current device.
+static inline bool ias_first_use_on_device(unsigned long long& seen) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+  const unsigned long long bit = 1ull << dev;
+  if (seen & bit) return false;
+  seen |= bit;
+  return true;
+}

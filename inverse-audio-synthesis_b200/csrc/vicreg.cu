@@ -776,11 +776,10 @@ int check_common(const float* x, int B, int D, void* ws, size_t ws_bytes, const 
 }
 
 int launch_gram(const Plan& p, float* w, cudaStream_t st) {
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;
   const int smem = (int)sizeof(GramSmem) + 1024;
-  if (!attr_set) {
+  if (ias_first_use_on_device(attr_devs)) {
     IAS_CUDA(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   {
     ProfScope prof_(K_VICREG_GRAM_TC, st);
@@ -926,11 +925,10 @@ int run_backward(const float* x, const float* y, const Plan& p, int local_row0, 
     k_pack_offg<<<dim3(p.DT, 2), 256, 0, st>>>(w + p.off_gfull, p.Dp, w + p.off_gpack, p.DT);
   }
   IAS_LAUNCH_CHECK("k_pack_offg");
-  static bool attr_set = false;
+  static unsigned long long attr_devs = 0;
   const int smem = (int)sizeof(GramSmem) + 1024;
-  if (!attr_set) {
+  if (ias_first_use_on_device(attr_devs)) {
     IAS_CUDA(cudaFuncSetAttribute(k_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
   }
   BwdArgs a;
   a.x = x; a.y = y;

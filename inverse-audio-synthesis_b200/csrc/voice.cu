@@ -855,11 +855,10 @@ int launch_control(const float* params01, int B, int C, float cr, float eps, con
   {
     // 4 s clips: phase + output rows in shared memory (7*C floats); longer clips fall back to global scratch rows
     const size_t smem = (size_t)7 * C * sizeof(float);
-    static bool attr_set = false;
+    static unsigned long long attr_devs = 0;
     constexpr size_t SMEM_LIMIT = 56 * 1024;  // four CTAs per SM
-    if (!attr_set) {
+    if (ias_first_use_on_device(attr_devs)) {
       IAS_CUDA(cudaFuncSetAttribute(k_voice_control<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-      attr_set = true;
     }
     ProfScope prof_(K_VOICE_CONTROL, st);
     if (smem <= SMEM_LIMIT)
@@ -874,12 +873,9 @@ int launch_control(const float* params01, int B, int C, float cr, float eps, con
 }
 
 int sm_count() {
-  static const int n = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
+  int dev = 0, v = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  return v;
 }
 
 // Shape of the audio kernel: threads per CTA, samples per thread per tile, resident CTAs per SM.

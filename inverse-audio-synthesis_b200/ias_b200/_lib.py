@@ -163,6 +163,14 @@ def current_stream(device) -> c_void_p:
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def on_device(t):
+    """Context manager making ``t``'s GPU the current CUDA device for the duration of a library call: kernels launch on
+    the calling thread's current device, which need not be the tensor's when a process drives several GPUs."""
+    import torch
+
+    return torch.cuda.device(t.device)
+
+
 def require_cuda(t, name: str) -> None:
     if not t.is_cuda:
         raise IasError(
@@ -172,6 +180,6 @@ def require_cuda(t, name: str) -> None:
 
 
 __all__ = [
-    "IasError", "build", "lib", "comm_lib", "check", "check_comm", "ptr", "current_stream", "require_cuda",
+    "IasError", "build", "lib", "comm_lib", "check", "check_comm", "ptr", "current_stream", "require_cuda", "on_device",
     "LIB_PATH", "COMM_LIB_PATH", "NPARAMS", "NCONTROL", "CORE_SYMBOLS", "COMM_SYMBOLS", "c_uint8",
 ]

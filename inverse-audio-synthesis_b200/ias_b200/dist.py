@@ -136,9 +136,10 @@ class FusedGatherLoss(torch.autograd.Function):
         ex.publish(x.float(), y.float())
         ws = ex.ws()
         out4 = torch.empty(4, dtype=torch.float32, device=x.device)
-        rc = _lib.lib().ias_vicreg_loss_gather(ex.x_ptrs, ex.y_ptrs, ex.world, ex.rank, ex.b_local, cfg_batch, ex.D,
-                                               embeddim, sim, stdc, covc, _lib.ptr(out4), _lib.ptr(ws), ws.numel() * 4,
-                                               _lib.current_stream(x.device))
+        with _lib.on_device(x):
+            rc = _lib.lib().ias_vicreg_loss_gather(ex.x_ptrs, ex.y_ptrs, ex.world, ex.rank, ex.b_local, cfg_batch, ex.D,
+                                                   embeddim, sim, stdc, covc, _lib.ptr(out4), _lib.ptr(ws),
+                                                   ws.numel() * 4, _lib.current_stream(x.device))
         _lib.check(rc, "ias_vicreg_loss_gather")
         ctx.ex, ctx.args = ex, (cfg_batch, embeddim, sim, stdc, covc)
         return out4[0], out4[1], out4[2], out4[3]
@@ -152,8 +153,10 @@ class FusedGatherLoss(torch.autograd.Function):
         gx = torch.empty((ex.b_local, ex.D), dtype=torch.float32, device=ex.device)
         gy = torch.empty_like(gx)
         ws = ex.ws()
-        rc = _lib.lib().ias_vicreg_loss_gather_backward(ex.world, ex.rank, ex.b_local, cfg_batch, ex.D, embeddim, sim,
-                                                        stdc, covc, _lib.ptr(gout), _lib.ptr(gx), _lib.ptr(gy),
-                                                        _lib.ptr(ws), ws.numel() * 4, _lib.current_stream(ex.device))
+        with _lib.on_device(gx):
+            rc = _lib.lib().ias_vicreg_loss_gather_backward(ex.world, ex.rank, ex.b_local, cfg_batch, ex.D, embeddim,
+                                                            sim, stdc, covc, _lib.ptr(gout), _lib.ptr(gx), _lib.ptr(gy),
+                                                            _lib.ptr(ws), ws.numel() * 4,
+                                                            _lib.current_stream(ex.device))
         _lib.check(rc, "ias_vicreg_loss_gather_backward")
         return gx, gy, None, None, None, None, None, None

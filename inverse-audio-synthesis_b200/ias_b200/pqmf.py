@@ -123,14 +123,17 @@ class PQMF(nn.Module):
         if _norm is not None:
             mean_t, std_t = _norm
             norm_dev = torch.cat([mean_t, std_t]).to(x.device)
-            rc = lib.ias_pqmf_analysis_image(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto), _lib.ptr(mod),
-                                             _lib.ptr(row_scale), _lib.ptr(mean_t), _lib.ptr(std_t), _lib.ptr(norm_dev),
-                                             _lib.ptr(out), B, T, self.N, K, _lib.current_stream(x.device))
+            with _lib.on_device(x):
+                rc = lib.ias_pqmf_analysis_image(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto),
+                                                 _lib.ptr(mod), _lib.ptr(row_scale), _lib.ptr(mean_t), _lib.ptr(std_t),
+                                                 _lib.ptr(norm_dev), _lib.ptr(out), B, T, self.N, K,
+                                                 _lib.current_stream(x.device))
             _lib.check(rc, "ias_pqmf_analysis_image")
             return out
-        rc = lib.ias_pqmf_analysis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto), _lib.ptr(mod),
-                                   _lib.ptr(row_scale), _lib.ptr(out), B, T, self.N, K,
-                                   _lib.current_stream(x.device))
+        with _lib.on_device(x):
+            rc = lib.ias_pqmf_analysis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto), _lib.ptr(mod),
+                                       _lib.ptr(row_scale), _lib.ptr(out), B, T, self.N, K,
+                                       _lib.current_stream(x.device))
         _lib.check(rc, "ias_pqmf_analysis")
         return out
 
@@ -146,8 +149,9 @@ class PQMF(nn.Module):
         dev, host, _ = self._taps("G")
         K = host.shape[1]
         out = torch.empty((B, 1, L * self.N), dtype=torch.float32, device=x.device)
-        rc = _lib.lib().ias_pqmf_synthesis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(out), B, L, self.N, K,
-                                           _lib.current_stream(x.device))
+        with _lib.on_device(x):
+            rc = _lib.lib().ias_pqmf_synthesis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(out), B, L, self.N,
+                                               K, _lib.current_stream(x.device))
         _lib.check(rc, "ias_pqmf_synthesis")
         # conv1d(padding=taps//2) keeps L*N samples for even `taps` (the default) and drops the last one for odd
         keep = L * self.N + 2 * (self.taps // 2) - self.taps

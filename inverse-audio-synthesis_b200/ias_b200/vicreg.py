@@ -97,9 +97,10 @@ class _VicregLossFn(torch.autograd.Function):
         lib = _lib.lib()
         ws = holder.workspace(B, D, xc.device)
         out4 = torch.empty(4, dtype=torch.float32, device=xc.device)
-        rc = lib.ias_vicreg_loss(_lib.ptr(xc), _lib.ptr(yc), B, local_row0, b_local, cfg_batch, D, embeddim, sim, stdc,
-                                 covc, _lib.ptr(out4), _lib.ptr(ws), ws.numel() * ws.element_size(),
-                                 _lib.current_stream(xc.device))
+        with _lib.on_device(xc):
+            rc = lib.ias_vicreg_loss(_lib.ptr(xc), _lib.ptr(yc), B, local_row0, b_local, cfg_batch, D, embeddim, sim,
+                                     stdc, covc, _lib.ptr(out4), _lib.ptr(ws), ws.numel() * ws.element_size(),
+                                     _lib.current_stream(xc.device))
         _lib.check(rc, "ias_vicreg_loss")
         ctx.save_for_backward(xc, yc)
         ctx.args = (B, local_row0, b_local, cfg_batch, D, embeddim, sim, stdc, covc)
@@ -116,10 +117,11 @@ class _VicregLossFn(torch.autograd.Function):
         gx = torch.empty_like(xc)
         gy = torch.empty_like(yc)
         ws = ctx.ws
-        rc = _lib.lib().ias_vicreg_loss_backward(
-            _lib.ptr(xc), _lib.ptr(yc), B, local_row0, b_local, cfg_batch, D, embeddim, sim, stdc, covc,
-            _lib.ptr(gout), _lib.ptr(gx), _lib.ptr(gy), _lib.ptr(ws), ws.numel() * ws.element_size(),
-            _lib.current_stream(xc.device))
+        with _lib.on_device(xc):
+            rc = _lib.lib().ias_vicreg_loss_backward(
+                _lib.ptr(xc), _lib.ptr(yc), B, local_row0, b_local, cfg_batch, D, embeddim, sim, stdc, covc,
+                _lib.ptr(gout), _lib.ptr(gx), _lib.ptr(gy), _lib.ptr(ws), ws.numel() * ws.element_size(),
+                _lib.current_stream(xc.device))
         _lib.check(rc, "ias_vicreg_loss_backward")
         return gx, gy, None, None, None, None, None, None, None, None
 

@@ -375,14 +375,16 @@ class Voice(nn.Module):
             # the batch number stays on the device: no host read-back, and the call can be captured in a CUDA graph
             if seed.dtype != torch.int64 or seed.numel() != 1:
                 raise ValueError("a device-resident batch index must be a single int64")
-            rc = _lib.lib().ias_voice_seed_params_dev(
-                _lib.ptr(seed), self.batch_size, frozen, _lib.ptr(self._store), _lib.ptr(self._is_train),
-                _lib.current_stream(self.device))
+            with _lib.on_device(self._store):
+                rc = _lib.lib().ias_voice_seed_params_dev(
+                    _lib.ptr(seed), self.batch_size, frozen, _lib.ptr(self._store), _lib.ptr(self._is_train),
+                    _lib.current_stream(self.device))
             _lib.check(rc, "ias_voice_seed_params_dev")
             return
-        rc = _lib.lib().ias_voice_seed_params(
-            int(seed) * self.batch_size, self.batch_size, frozen, _lib.ptr(self._store), _lib.ptr(self._is_train),
-            _lib.current_stream(self.device))
+        with _lib.on_device(self._store):
+            rc = _lib.lib().ias_voice_seed_params(
+                int(seed) * self.batch_size, self.batch_size, frozen, _lib.ptr(self._store), _lib.ptr(self._is_train),
+                _lib.current_stream(self.device))
         _lib.check(rc, "ias_voice_seed_params")
 
     def _frozen_rows(self) -> List[int]:
@@ -402,12 +404,12 @@ class Voice(nn.Module):
         if self._peak is None or self._peak.device != self.device:
             self._peak = torch.empty(cfg.batch_size, dtype=torch.float32, device=self.device)
         ws = self._ws()
-        rc = _lib.lib().ias_voice_render(
-            _lib.ptr(self._store), _lib.ptr(noise), noise.shape[0], _lib.ptr(audio), _lib.ptr(self._peak),
-            cfg.batch_size, cfg.buffer_size, cfg.control_buffer_size, float(cfg.sample_rate), float(cfg.control_rate),
-            float(cfg.eps), 1 if self.normalize else 0, _lib.ptr(ctrl_in), _lib.ptr(phase_debug), _lib.ptr(ws),
-            ws.numel(),
-            _lib.current_stream(self.device))
+        with _lib.on_device(self._store):
+            rc = _lib.lib().ias_voice_render(
+                _lib.ptr(self._store), _lib.ptr(noise), noise.shape[0], _lib.ptr(audio), _lib.ptr(self._peak),
+                cfg.batch_size, cfg.buffer_size, cfg.control_buffer_size, float(cfg.sample_rate),
+                float(cfg.control_rate), float(cfg.eps), 1 if self.normalize else 0, _lib.ptr(ctrl_in),
+                _lib.ptr(phase_debug), _lib.ptr(ws), ws.numel(), _lib.current_stream(self.device))
         _lib.check(rc, "ias_voice_render")
         return (audio, self._peak) if return_peak else audio
 
@@ -419,9 +421,10 @@ class Voice(nn.Module):
         ctrl = torch.empty((cfg.batch_size, _lib.NCONTROL, cfg.control_buffer_size), dtype=torch.float32,
                            device=self.device)
         ws = self._ws()
-        rc = _lib.lib().ias_voice_control(
-            _lib.ptr(self._store), cfg.batch_size, cfg.control_buffer_size, float(cfg.control_rate), float(cfg.eps),
-            _lib.ptr(ctrl), _lib.ptr(ws), ws.numel(), _lib.current_stream(self.device))
+        with _lib.on_device(self._store):
+            rc = _lib.lib().ias_voice_control(
+                _lib.ptr(self._store), cfg.batch_size, cfg.control_buffer_size, float(cfg.control_rate), float(cfg.eps),
+                _lib.ptr(ctrl), _lib.ptr(ws), ws.numel(), _lib.current_stream(self.device))
         _lib.check(rc, "ias_voice_control")
         return ctrl
 

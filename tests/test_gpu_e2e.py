@@ -116,3 +116,33 @@ def test_device_batch_index_and_cuda_graph_replay(cuda_device):
         torch.cuda.synchronize()
         for a, b in zip(static, w):
             assert torch.equal(a, b)
+
+
+def test_second_device_in_the_same_process(cuda_device):
+    """One process driving two GPUs: calls made while cuda:0 is the current device must still run on the GPU that
+    holds the tensors (the bindings switch device around every library call; opt-in shared memory is set per device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ias_b200
+
+    B = 32
+    outs = []
+    for dev in (torch.device("cuda:0"), torch.device("cuda:1")):
+        cfg = ias_b200.SynthConfig(batch_size=B, reproducible=True, sample_rate=44100, buffer_size_seconds=4.0)
+        voice = ias_b200.Voice(synthconfig=cfg).to(dev)
+        gram = ias_b200.PQMF(N=3).to(dev)
+        vcfg = types.SimpleNamespace(dim=256, embeddim=256, vicreg=types.SimpleNamespace(
+            mlp="8-8-%d", batch_size=B, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
+        vic = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity(), gather=False)
+        wa, wp = harness.bridge_weights(dev)
+        assert torch.cuda.current_device() == 0
+        audio, params, _ = voice(2)
+        bands = gram(audio.unsqueeze(1))
+        x, y = harness.bridge(bands, params, wa, wp)
+        x.requires_grad_(True)
+        loss = vic.loss(x, y)
+        loss[0].backward()
+        assert audio.device == dev and bands.device == dev and loss[0].device == dev
+        outs.append((audio.cpu(), bands.cpu(), torch.stack([l.detach() for l in loss]).cpu(), x.grad.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
