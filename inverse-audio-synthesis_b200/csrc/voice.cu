@@ -161,7 +161,7 @@ k_voice_adsr(const float* __restrict__ params01, int B, int C, float cr, float e
              float* __restrict__ env) {
   __shared__ float s_v[6];  // attack, decay, sustain, release, alpha, keyboard duration (through from_0to1)
   __shared__ Adsr s_adsr;
-  const int e = blockIdx.x, b = blockIdx.y;
+  const int b = blockIdx.x, e = blockIdx.y;  // voices on x: no 65535 limit on the batch
   const int tid = threadIdx.x;
   const int base[6] = {ADSR1, ADSR2, LFO1_AMP, LFO2_AMP, LFO1_RATE, LFO2_RATE};
   if (tid < 6) {
@@ -849,7 +849,7 @@ int launch_control(const float* params01, int B, int C, float cr, float eps, con
   static const RangeTable ranges = make_range_table();
   {
     ProfScope prof_(K_VOICE_ADSR, st);
-    k_voice_adsr<<<dim3(6, B), ADSR_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, w.scratch);
+    k_voice_adsr<<<dim3(B, 6), ADSR_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, w.scratch);
   }
   IAS_LAUNCH_CHECK("k_voice_adsr");
   {
