@@ -498,14 +498,11 @@ __device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
 // vm::vco_increment for two samples: 2*pi*hz(clamp(midi + depth*mod, 0, 127)) / sample_rate, same op order.
 template <bool CLAMP>
 __device__ __forceinline__ P2 vco_increment_p2(float midi, float depth, P2 mod, float sr, float rsr) {
-  const P2 dm = p2_mul(p2b(depth), mod);
-  // scalar adds: the product keeps its own rounding (see the note on contraction above)
-  float m0 = add(midi, p2lo(dm)), m1 = add(midi, p2hi(dm));
-  if (CLAMP) {  // voices whose range is provably inside (VC_NOCLAMP) skip the four min/max instructions
-    m0 = fminf(fmaxf(m0, 0.0f), 127.0f);
-    m1 = fminf(fmaxf(m1, 0.0f), 127.0f);
-  }
-  const P2 a = p2_add(p2(m0, m1), p2b(-69.0f));
+  // depth * mod in scalar form, so that the product keeps its own rounding (see the note on contraction above)
+  P2 m = p2_add(p2b(midi), p2(mul(depth, p2lo(mod)), mul(depth, p2hi(mod))));
+  if (CLAMP)  // voices whose range is provably inside (VC_NOCLAMP) skip the four min/max instructions
+    m = p2(fminf(fmaxf(p2lo(m), 0.0f), 127.0f), fminf(fmaxf(p2hi(m), 0.0f), 127.0f));
+  const P2 a = p2_add(m, p2b(-69.0f));
   // a / 12: Markstein step with RN(1/12)  (div_const)
   const P2 q = p2_mul(a, p2b(0.0833333358168601989746f));
   const P2 d = p2_fma(p2_fma(q, p2b(-12.0f), a), p2b(0.0833333358168601989746f), q);
