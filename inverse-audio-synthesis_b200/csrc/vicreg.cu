@@ -227,8 +227,17 @@ __global__ void __launch_bounds__(256) k_center_pack(const float* __restrict__ x
   for (int d = threadIdx.x; d < DT * TILE; d += blockDim.x) {
     float mean = 0.0f;
     if (d < D) {
+      // P column-sum partials (64 at B = 8192): eight loads in flight, summed in index order as before
       float t = 0.0f;
-      for (int p = 0; p < P; ++p) t += partial[((size_t)p * 2 + s) * D + d];
+      int p = 0;
+      for (; p + 8 <= P; p += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = partial[((size_t)(p + u) * 2 + s) * D + d];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t += v[u];
+      }
+      for (; p < P; ++p) t += partial[((size_t)p * 2 + s) * D + d];
       mean = t * invB;
       if (pb == 0) mean_out[s * D + d] = mean;
     }
@@ -708,12 +717,19 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(FinalArgs a) {
     for (int s = 0; s < 2; ++s) {
       float acc0 = 0.0f, acc1 = 0.0f;
       if (d < a.D) {
+        constexpr int UV = 8;  // partials in flight per thread: the loop is a chain of L2 round trips otherwise
         int p = part;
-        for (; p + 4 < a.NV; p += 8) {
-          acc0 += a.varpart[((size_t)p * 2 + s) * a.D + d];
-          acc1 += a.varpart[((size_t)(p + 4) * 2 + s) * a.D + d];
+        for (; p + 4 * (UV - 1) < a.NV; p += 4 * UV) {
+          float v[UV];
+#pragma unroll
+          for (int u = 0; u < UV; ++u) v[u] = a.varpart[((size_t)(p + 4 * u) * 2 + s) * a.D + d];
+#pragma unroll
+          for (int u = 0; u < UV; u += 2) {
+            acc0 += v[u];
+            acc1 += v[u + 1];
+          }
         }
-        if (p < a.NV) acc0 += a.varpart[((size_t)p * 2 + s) * a.D + d];
+        for (; p < a.NV; p += 4) acc0 += a.varpart[((size_t)p * 2 + s) * a.D + d];
       }
       s_var[part][col] = acc0 + acc1;
       __syncthreads();
