@@ -12,6 +12,7 @@
 // HBM traffic: 4T read + 4T written per sound in each direction (algorithmic minimum).
 #include "ias_common.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -33,6 +34,22 @@ struct TapsCM {
   float g[K];
   float c[N * 2 * N];
 };
+
+// For N >= 8 the N x 2N cosine modulation is evaluated as one size-N DCT-IV on folded partial sums.  With
+// t = r - (K-2)/2, every residue r maps to t' = t + 2N*q in {+-(m + 1/2)}, m < N, with sign (-1)^q (the cosine flips
+// sign every 2N taps for all k).  Writing P[m] / Q[m] for the signed partial sums at t' = +(m+1/2) / -(m+1/2):
+//   out[k] = sum_m cos((2k+1)(2m+1)pi/(4N)) / sqrt(2) * ( (P[m] + Q[m]) - (P[N-1-m] - Q[N-1-m]) )
+// (the (-1)^k pi/4 phase of pqmf.py:28 turns the sine part into the index-reversed cosine part): N^2 + 3N instead of
+// 2N^2 operations per time step.  For N >= 8 TapsCM::c holds that N x N matrix in its first N*N entries.
+template <int N, int K>
+struct FoldCM {
+  __host__ __device__ static constexpr int wrap(int x) { return ((x % (2 * N)) + 2 * N) % (2 * N); }
+  __host__ __device__ static constexpr int rP(int m) { return wrap(m + (K - 1) / 2); }
+  __host__ __device__ static constexpr int rQ(int m) { return wrap((K - 3) / 2 - m); }
+  __host__ __device__ static constexpr bool negP(int m) { return (((m + (K - 1) / 2) - rP(m)) / (2 * N)) & 1; }
+  __host__ __device__ static constexpr bool negQ(int m) { return ((((K - 3) / 2 - m) - rQ(m)) / (2 * N)) & 1; }
+};
+constexpr int FOLD_MIN_N = 8;
 
 // Optional per-band epilogue (band - mean[k]) / std[k]: torchvision.transforms.Normalize on the [B,3,240,245] image
 // view the reference takes of the bands (audioembed.py:41,49; constants vicreg_audio_params.py:60-62).
@@ -189,12 +206,33 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
     for (int j = 0; j < K; ++j)
 #pragma unroll
       for (int q = 0; q < Q; ++q) ps[q][j % (2 * N)] = fmaf(taps.g[j], w[q * N + j], ps[q][j % (2 * N)]);
+    if constexpr (N >= FOLD_MIN_N) {
+      using F = FoldCM<N, K>;
 #pragma unroll
-    for (int r = 0; r < 2 * N; ++r)
+      for (int q = 0; q < Q; ++q) {
+        float sum[N], dif[N];  // P + Q and P - Q with the residue signs applied
 #pragma unroll
-      for (int k = 0; k < N; ++k)
+        for (int m = 0; m < N; ++m) {
+          const float pm = F::negP(m) ? -ps[q][F::rP(m)] : ps[q][F::rP(m)];
+          const float qm = F::negQ(m) ? -ps[q][F::rQ(m)] : ps[q][F::rQ(m)];
+          sum[m] = pm + qm;
+          dif[m] = pm - qm;
+        }
 #pragma unroll
-        for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.c[k * 2 * N + r], ps[q][r], acc[q][k]);
+        for (int m = 0; m < N; ++m) {
+          const float v = sum[m] - dif[N - 1 - m];
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc[q][k] = fmaf(taps.c[k * N + m], v, acc[q][k]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 2 * N; ++r)
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+          for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.c[k * 2 * N + r], ps[q][r], acc[q][k]);
+    }
   }
 
   if (row_scale) {
@@ -375,7 +413,15 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
   if (proto_host && mod_host) {
     TapsCM<N, K> taps;
     for (int i = 0; i < K; ++i) taps.g[i] = proto_host[i];
-    for (int i = 0; i < N * 2 * N; ++i) taps.c[i] = mod_host[i];
+    if (N >= FOLD_MIN_N) {  // the folded form needs only N: cos((2k+1)(2m+1)pi/(4N)) / sqrt(2)
+      for (int i = 0; i < N * 2 * N; ++i) taps.c[i] = 0.0f;
+      for (int k = 0; k < N; ++k)
+        for (int m = 0; m < N; ++m)
+          taps.c[k * N + m] = (float)(cos((2.0 * k + 1.0) * (2.0 * m + 1.0) * 3.14159265358979323846 / (4.0 * N)) *
+                                      0.70710678118654752440);
+    } else {
+      for (int i = 0; i < N * 2 * N; ++i) taps.c[i] = mod_host[i];
+    }
     k_pqmf_analysis<N, K, Q, TapsCM<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm);
   } else {
     Taps<N, K> taps;
