@@ -127,9 +127,11 @@ IAS_API int ias_pqmf_analysis_image(const float* x, const float* H_dev, const fl
                             ias_stream_t stream);
 
 /* PQMF.synthesis (pqmf.py:52-55): zero-stuff by N with gain N, then the N->1 FIR G = [N][K] (buffer G[0]).
- * y[b][t], t < L*N. */
-IAS_API int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, float* y, int B, int L, int N, int K,
-                       ias_stream_t stream);
+ * y[b][t], t < L*N.  proto_host[K] (host, optional) is the same signed prototype as in ias_pqmf_analysis: the caller
+ * passes it when G is the filter PQMF.__init__ designs (pqmf.py:18-30), and N = 8 / 16 then run the cosine-modulated
+ * form (size-N DCT-IV per time step + 63 multiply-adds, instead of 63 N); NULL = direct form, valid for any G. */
+IAS_API int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, const float* proto_host, float* y,
+                       int B, int L, int N, int K, ias_stream_t stream);
 
 /* ---- VICReg loss: vicreg.VICReg.loss / off_diagonal (vicreg.py:35-58,73-76) ------------------------------ */
 

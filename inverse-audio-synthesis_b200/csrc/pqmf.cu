@@ -376,6 +376,116 @@ k_pqmf_synthesis(const float* __restrict__ z, float* __restrict__ y, int L, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// synthesis, cosine-modulated form (N >= 8, G = the filter PQMF.__init__ designs, pqmf.py:18-30):
+//   G[k][j] = g[j] * cos(theta_k (r - (K-2)/2) - (-1)^k pi/4), r = j mod 2N, g[j] = (-1)^floor(j/2N) 2 prototype[j]
+//   v[m][r]  = sum_k cos(...) * N z[k][m]                         (modulation of time step m, shared by all taps)
+//   y[nN+p]  = sum_{j : p(j) = p} g[j] * v[n + o(j)][j mod 2N]    (63 multiply-adds per time step)
+// and the N -> 2N modulation is one size-N DCT-IV U[m'] = sum_k C[k][m'] z[k] unfolded with signs: with
+// r - (K-2)/2 + 2N q = +-(m' + 1/2),  v[r] = (-1)^q (N / sqrt 2) (U[m'] +- U[N-1-m'])  (the -(-1)^k pi/4 phase turns
+// the sine part into the index-reversed cosine part).  N^2 + 2N + 63 instead of 63 N operations per time step
+// (N = 16: 351 instead of 1008).
+// Phase 1: thread = one time step of the tile + halo; its N band values come straight from global memory (coalesced
+// over time), DCT-IV from the constant bank, 2N modulated values to shared memory (row pitch 2N+4 floats: the 128-bit
+// accesses of a quarter warp fall into 8 distinct bank groups).  Phase 2: thread = one time step, N outputs, its
+// 63 (row, r) operands read as 128-bit shared loads.
+// ------------------------------------------------------------------------------------------------------------
+template <int N, int K>
+struct TapsSynCM {
+  float g[K];
+  float c[N * N];  // (N / sqrt 2) cos((2k+1)(2m+1) pi / (4N)), [k][m]
+};
+
+template <int N, int K>
+struct UnfoldCM {
+  // twice (r - (K-2)/2) wrapped into (-2N, 2N): an odd integer
+  __host__ __device__ static constexpr int tt(int r) {
+    return ((2 * r - (K - 2) + 2 * N) % (4 * N) + 4 * N) % (4 * N) - 2 * N;
+  }
+  __host__ __device__ static constexpr int mp(int r) { return ((tt(r) < 0 ? -tt(r) : tt(r)) - 1) / 2; }
+  __host__ __device__ static constexpr bool pos(int r) { return tt(r) > 0; }
+  __host__ __device__ static constexpr bool neg(int r) { return (((tt(r) - (2 * r - (K - 2))) / (4 * N)) & 1) != 0; }
+};
+
+template <int N, int K>
+__global__ void __launch_bounds__(PQ_THREADS)
+k_pqmf_synthesis_cm(const float* __restrict__ z, float* __restrict__ y, int L, int tiles_per_row, TapsSynCM<N, K> taps) {
+  using Geo = SynthGeom<N, K>;
+  using UF = UnfoldCM<N, K>;
+  constexpr int DMIN = Geo::omin();
+  constexpr int HALO = Geo::omax() - DMIN;
+  constexpr int TILE_N = PQ_THREADS - HALO;  // time steps per CTA; every thread modulates one row
+  constexpr int PITCH = 2 * N + 4;
+  static_assert(N % 4 == 0, "128-bit rows");
+  __shared__ __align__(16) float vs[PQ_THREADS * PITCH];
+
+  const int b = blockIdx.x / tiles_per_row;
+  const int tile = blockIdx.x - b * tiles_per_row;
+  const int n_tile = tile * TILE_N;
+
+  {
+    const int m = n_tile + DMIN + (int)threadIdx.x;
+    float zk[N];
+    const bool in = (m >= 0 && m < L);
+    const float* zp = z + (size_t)b * N * L + (in ? m : 0);
+#pragma unroll
+    for (int k = 0; k < N; ++k) zk[k] = in ? __ldg(zp + (size_t)k * L) : 0.0f;
+    float u[N];
+#pragma unroll
+    for (int mm = 0; mm < N; ++mm) u[mm] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+      for (int mm = 0; mm < N; ++mm) u[mm] = fmaf(taps.c[k * N + mm], zk[k], u[mm]);
+    float v[2 * N];
+#pragma unroll
+    for (int r = 0; r < 2 * N; ++r) {
+      const float a = u[UF::mp(r)], bb = u[N - 1 - UF::mp(r)];
+      const float s = UF::pos(r) ? a + bb : a - bb;
+      v[r] = UF::neg(r) ? -s : s;
+    }
+    float* row = vs + threadIdx.x * PITCH;
+#pragma unroll
+    for (int r = 0; r < 2 * N; r += 4) *reinterpret_cast<float4*>(row + r) = make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+  }
+  __syncthreads();
+
+  if ((int)threadIdx.x >= TILE_N) return;
+  const int n0 = n_tile + (int)threadIdx.x;
+  if (n0 >= L) return;
+  float acc[N];
+#pragma unroll
+  for (int p = 0; p < N; ++p) acc[p] = 0.0f;
+#pragma unroll
+  for (int rho = 0; rho <= HALO; ++rho) {
+    // operands of this row: taps j with o(j) - DMIN == rho, at r = j mod 2N
+    const float* row = vs + ((int)threadIdx.x + rho) * PITCH;
+    float w[2 * N];
+#pragma unroll
+    for (int r4 = 0; r4 < 2 * N; r4 += 4) {
+      bool need = false;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if (Geo::offset(j) - DMIN == rho && (j % (2 * N)) / 4 == r4 / 4) need = true;
+      if (need) {
+        const float4 t = *reinterpret_cast<const float4*>(row + r4);
+        w[r4] = t.x; w[r4 + 1] = t.y; w[r4 + 2] = t.z; w[r4 + 3] = t.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (Geo::offset(j) - DMIN == rho) acc[Geo::phase(j)] = fmaf(taps.g[j], w[j % (2 * N)], acc[Geo::phase(j)]);
+  }
+  float* yo = y + (size_t)b * L * N + (size_t)n0 * N;
+  if ((reinterpret_cast<uintptr_t>(y) & 15u) == 0 && (((size_t)L * N) % 4 == 0)) {
+#pragma unroll
+    for (int p = 0; p < N; p += 4) *reinterpret_cast<float4*>(yo + p) = make_float4(acc[p], acc[p + 1], acc[p + 2], acc[p + 3]);
+  } else {
+#pragma unroll
+    for (int p = 0; p < N; ++p) yo[p] = acc[p];
+  }
+}
+
 __global__ void k_pqmf_synthesis_generic(const float* __restrict__ z, const float* __restrict__ G,
                                          float* __restrict__ y, int B, int L, int N, int K) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -446,6 +556,24 @@ int launch_synthesis(const float* z, const float* G_host, float* y, int B, int L
   return IAS_OK;
 }
 
+template <int N, int K>
+int launch_synthesis_cm(const float* z, const float* proto_host, float* y, int B, int L, cudaStream_t st) {
+  TapsSynCM<N, K> taps;
+  for (int i = 0; i < K; ++i) taps.g[i] = proto_host[i];
+  for (int k = 0; k < N; ++k)
+    for (int m = 0; m < N; ++m)
+      taps.c[k * N + m] = (float)(cos((2.0 * k + 1.0) * (2.0 * m + 1.0) * 3.14159265358979323846 / (4.0 * N)) *
+                                  0.70710678118654752440 * N);
+  constexpr int TILE_N = PQ_THREADS - (SynthGeom<N, K>::omax() - SynthGeom<N, K>::omin());
+  const int tiles = (L + TILE_N - 1) / TILE_N;
+  {
+    ProfScope prof_(K_PQMF_SYNTHESIS, st);
+    k_pqmf_synthesis_cm<N, K><<<(unsigned)((size_t)B * tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_synthesis_cm");
+  return IAS_OK;
+}
+
 }  // namespace
 }  // namespace ias
 
@@ -513,12 +641,16 @@ extern "C" int ias_pqmf_analysis_image(const float* x, const float* H_dev, const
                         K, stream, "ias_pqmf_analysis_image");
 }
 
-extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, float* y, int B, int L,
-                                  int N, int K, ias_stream_t stream) {
+extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, const float* proto_host,
+                                  float* y, int B, int L, int N, int K, ias_stream_t stream) {
   IAS_REQUIRE(B > 0 && L > 0 && N > 0 && K > 0, IAS_ERR_INVALID, "ias_pqmf_synthesis: B=%d L=%d N=%d K=%d", B, L, N, K);
   IAS_REQUIRE(z && y, IAS_ERR_INVALID, "ias_pqmf_synthesis: NULL pointer");
   IAS_REQUIRE(G_dev || G_host, IAS_ERR_INVALID, "ias_pqmf_synthesis: no filter given");
   cudaStream_t st = as_stream(stream);
+  if (proto_host && K == 63) {  // G is the designed filter: cosine-modulated form
+    if (N == 16) return launch_synthesis_cm<16, 63>(z, proto_host, y, B, L, st);
+    if (N == 8) return launch_synthesis_cm<8, 63>(z, proto_host, y, B, L, st);
+  }
   if (G_host && K == 63) {
     int q = 0;  // IAS_PQMF_SYNTH_Q: tuning override of the time steps per thread
     if (const char* e = getenv("IAS_PQMF_SYNTH_Q")) q = atoi(e);

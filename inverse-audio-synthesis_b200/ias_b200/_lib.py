@@ -65,7 +65,8 @@ _SIGNATURES = {
                                   c_int, c_int, c_void_p]),
     "ias_pqmf_analysis_image": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "ias_pqmf_synthesis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ias_pqmf_synthesis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_void_p]),
     "ias_vicreg_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ias_vicreg_loss": (
         c_int,

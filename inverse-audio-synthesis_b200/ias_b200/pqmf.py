@@ -71,11 +71,11 @@ class PQMF(nn.Module):
             dev = buf.reshape(self.N, -1).contiguous()
             host = dev.detach().to("cpu", torch.float32).contiguous()
             factors = None
-            if which == "H":
-                H, _ = design_filters(self.N, self.taps, self.cutoff, self.beta)
-                if torch.equal(host, torch.from_numpy(H).float()):
-                    g, c = cosine_modulation_factors(self.N, self.taps, self.cutoff, self.beta)
-                    factors = (torch.from_numpy(g).contiguous(), torch.from_numpy(c).contiguous())
+            H, G = design_filters(self.N, self.taps, self.cutoff, self.beta)
+            if torch.equal(host, torch.from_numpy(H if which == "H" else G).float()):
+                # the synthesis bank shares the signed prototype; its modulation matrix is rebuilt by the kernel
+                g, c = cosine_modulation_factors(self.N, self.taps, self.cutoff, self.beta)
+                factors = (torch.from_numpy(g).contiguous(), torch.from_numpy(c).contiguous())
             hit = (key, dev, host, factors)
             self._host_cache[which] = hit
         return hit[1], hit[2], hit[3]
@@ -146,12 +146,13 @@ class PQMF(nn.Module):
             raise NotImplementedError("PQMF.synthesis has no backward")
         x = x.detach().to(torch.float32).contiguous()
         B, _, L = x.shape
-        dev, host, _ = self._taps("G")
+        dev, host, factors = self._taps("G")
+        proto = factors[0] if (factors is not None and self.polyphase) else None
         K = host.shape[1]
         out = torch.empty((B, 1, L * self.N), dtype=torch.float32, device=x.device)
         with _lib.on_device(x):
-            rc = _lib.lib().ias_pqmf_synthesis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(out), B, L, self.N,
-                                               K, _lib.current_stream(x.device))
+            rc = _lib.lib().ias_pqmf_synthesis(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto),
+                                               _lib.ptr(out), B, L, self.N, K, _lib.current_stream(x.device))
         _lib.check(rc, "ias_pqmf_synthesis")
         # conv1d(padding=taps//2) keeps L*N samples for even `taps` (the default) and drops the last one for odd
         keep = L * self.N + 2 * (self.taps // 2) - self.taps
