@@ -50,6 +50,21 @@ def bridge(bands: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torc
     return feat @ wa, params @ wp
 
 
+def analysis_bridge(gram, audio: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torch.Tensor):
+    """Device path of ``bridge(gram(audio), params)`` with the pooling fused into the PQMF analysis kernel
+    (``PQMF.analysis_pooled``): the bands make one trip to HBM.  -> (bands, x, y)."""
+    from ias_b200 import IasError
+
+    x3 = audio.unsqueeze(1) if audio.dim() == 2 else audio
+    try:
+        bands, feat = gram.analysis_pooled(x3, EMBED_DIM)
+    except IasError:  # bins narrower than a CTA tile (short clips): unfused device kernels, same result
+        bands = gram(x3)
+        x, y = bridge(bands, params, wa, wp)
+        return bands, x, y
+    return bands, feat @ wa, params @ wp
+
+
 def oracle_front_end(batch_idx: int, B: int, N: int = 3, seconds: float = 4.0, cfg_batch: int | None = None,
                      reproducible: bool = True, timings: Dict[str, float] | None = None, torch_ops: bool = False):
     """CPU oracle of one step: returns dict(audio, params, bands, x, y, loss4).  fp32 throughout, like config 1.

@@ -126,6 +126,18 @@ IAS_API int ias_pqmf_analysis_image(const float* x, const float* H_dev, const fl
                             const float* std_host, const float* norm_dev, float* out, int B, int T, int N, int K,
                             ias_stream_t stream);
 
+/* PQMF.analysis plus pooled band magnitudes -- harness bridge of SURVEY.md 8(d), not a reference surface:
+ * feat[b][i] = mean |bands_flat[b][floor(i S/P) .. ceil((i+1) S/P))| with S = N*L, i.e.
+ * torch.nn.functional.adaptive_avg_pool1d(out.abs().reshape(B,1,N*L), P), accumulated by the analysis CTAs while the
+ * band values are in registers (per-CTA partial sums in `workspace`, then a small fixed-order finalize kernel), so the
+ * bands are written once and not read back.  Requires a specialised kernel (N in {2,3,4,8,16}, K = 63, H_host given)
+ * and bins wider than its CTA tile; returns IAS_ERR_UNSUPPORTED otherwise (callers then pool with ias_abs_avg_pool).
+ * workspace >= ias_pqmf_pool_workspace_bytes(B, T, N, K) bytes of device memory. */
+IAS_API size_t ias_pqmf_pool_workspace_bytes(int B, int T, int N, int K);
+IAS_API int ias_pqmf_analysis_pooled(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
+                             const float* mod_host, const float* row_scale, float* out, float* feat, int P,
+                             void* workspace, size_t workspace_bytes, int B, int T, int N, int K, ias_stream_t stream);
+
 /* PQMF.synthesis (pqmf.py:52-55): zero-stuff by N with gain N, then the N->1 FIR G = [N][K] (buffer G[0]).
  * y[b][t], t < L*N.  proto_host[K] (host, optional) is the same signed prototype as in ias_pqmf_analysis: the caller
  * passes it when G is the filter PQMF.__init__ designs (pqmf.py:18-30), and N = 8 / 16 then run the cosine-modulated

@@ -60,6 +60,24 @@ struct BandNorm {
   int on;
 };
 
+// Optional pooled-magnitude epilogue (harness bridge, SURVEY 8d: adaptive_avg_pool1d(|bands|.reshape(B,1,N*L), P)):
+// while a CTA still holds its band values in registers it adds up |value| per pooling bin.  A CTA's TILE_N steps of one
+// band are TILE_N consecutive elements of the flattened [N*L] axis; with TILE_N + 1 <= floor(N*L / P) they touch at
+// most two bins, ilo = floor(first * P / (N*L)) and ilo + 1 (torch's bins [floor(i S/P), ceil((i+1) S/P)) overlap by
+// up to one element, which then counts for both).  The CTA writes the two sums to partial[b][k][tile][2] in a fixed
+// order (warp shuffle tree, then warps in order); k_pool_finalize adds each bin's few partials -- deterministic, and
+// the bands are not read back from HBM.
+struct PoolReq {  // host-side request of the pooled epilogue
+  float* feat;  // [B][P]
+  int P;
+  void* workspace;
+  size_t workspace_bytes;
+};
+struct PoolArgs {
+  float* partial;  // [B][N][tiles][2]
+  int P;
+  int S;  // N * L  (S * P < 2^31 is checked by the caller)
+};
 
 // Shared-memory layout of a staged signal row.  Thread t reads a sliding window that starts at linear index t*S.
 //   S % 4 == 0: rows are stored in chunks of S floats at a padded pitch SP (a multiple of 4 with SP/4 odd), so the
@@ -152,10 +170,10 @@ __device__ __forceinline__ void load_window(const float* __restrict__ src, float
 // ------------------------------------------------------------------------------------------------------------
 // analysis: out[b][k][n] = sum_j H[k][j] * x[b][n*N + j - PAD]
 // ------------------------------------------------------------------------------------------------------------
-template <int N, int K, int Q, class TapsT>
+template <int N, int K, int Q, class TapsT, bool POOL>
 __global__ void __launch_bounds__(PQ_THREADS)
 k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale, float* __restrict__ out, int T, int L,
-                int tiles_per_row, TapsT taps, BandNorm<N> norm) {
+                int tiles_per_row, TapsT taps, BandNorm<N> norm, PoolArgs pool) {
   constexpr int PAD = (K - 1) / 2;
   constexpr int S = Q * N;                 // input samples consumed per thread
   constexpr int WIN = (Q - 1) * N + K;     // input window of one thread
@@ -165,6 +183,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   constexpr int SPAN = TILE_N * N + K - N + 4;
   constexpr int SPAN4 = (SPAN + 3) / 4;
   __shared__ __align__(16) float xs[Pad<S>::floats(SPAN4 * 4)];
+  __shared__ int s_bound[POOL ? N : 1][2];                        // per band: start of bin ilo+1, end of bin ilo
+  __shared__ __align__(16) float s_pool[POOL ? 2 * N : 1][POOL ? PQ_THREADS : 4];  // per-thread sums, [band, slot] rows
 
   const int b = blockIdx.x / tiles_per_row;
   const int tile = blockIdx.x - b * tiles_per_row;
@@ -177,6 +197,16 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
     stage_row_interior<S, SPAN4>(xs, x + (size_t)b * T + g0);
   else
     stage_row<S, SPAN4>(xs, x + (size_t)b * T, g0, T, 1.0f, vec_ok);
+  if constexpr (POOL) {
+    if (threadIdx.x < N) {  // 32-bit arithmetic: S * P < 2^31 (checked by the launcher)
+      const unsigned first = (unsigned)((int)threadIdx.x * L + n_tile);
+      const unsigned ilo = (first * (unsigned)pool.P) / (unsigned)pool.S;
+      const unsigned num = (ilo + 1u) * (unsigned)pool.S;
+      const unsigned q = num / (unsigned)pool.P;
+      s_bound[threadIdx.x][0] = (int)q;
+      s_bound[threadIdx.x][1] = (int)(q + (num - q * (unsigned)pool.P != 0u ? 1u : 0u));
+    }
+  }
   __syncthreads();
 
   float w[WIN];
@@ -265,6 +295,69 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
         if (n0 + q < L) o[q] = acc[q][k];
     }
   }
+
+  if constexpr (POOL) {
+    const int warp = threadIdx.x >> 5;
+    const bool full = n_tile + TILE_N <= L;  // CTA-uniform: every step of the tile exists
+    const int nv = L - n0;                   // else: valid steps of this thread = min(nv, Q)
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const int s1 = s_bound[k][0], e0 = s_bound[k][1];
+      const int wfirst = k * L + n_tile + warp * 32 * Q, wlast = wfirst + 32 * Q - 1;
+      float a[Q];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) a[q] = (full || q < nv) ? fabsf(acc[q][k]) : 0.0f;
+      float sum0, sum1;
+      if (wlast < s1 || wfirst >= e0) {  // the whole warp lies in one bin (warp-uniform branch)
+        float t = a[0];
+#pragma unroll
+        for (int q = 1; q < Q; ++q) t += a[q];
+        sum0 = wlast < s1 ? t : 0.0f;
+        sum1 = wlast < s1 ? 0.0f : t;
+      } else {
+        const int f0 = k * L + n0;
+        sum0 = sum1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          sum0 += (f0 + q < e0) ? a[q] : 0.0f;
+          sum1 += (f0 + q >= s1) ? a[q] : 0.0f;
+        }
+      }
+      s_pool[2 * k][threadIdx.x] = sum0;
+      s_pool[2 * k + 1][threadIdx.x] = sum1;
+    }
+    __syncthreads();
+    // row r = (band, slot): 128 per-thread sums -> one value, fixed order (4 per lane, then a shuffle tree)
+    for (int r = warp; r < 2 * N; r += PQ_THREADS / 32) {
+      const int lane = threadIdx.x & 31;
+      const float4 v = *reinterpret_cast<const float4*>(&s_pool[r][4 * lane]);
+      float t = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) pool.partial[(((size_t)b * N + (r >> 1)) * tiles_per_row + tile) * 2 + (r & 1)] = t;
+    }
+  }
+}
+
+// feat[b][i] = mean of |bands_flat[b][s_i .. e_i)| from the per-CTA partial sums of the pooled analysis epilogue.
+__global__ void k_pool_finalize(const float* __restrict__ partial, float* __restrict__ feat, int B, int N, int L,
+                                int tiles, int tile_n, int P) {
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)(B * P)) return;
+  // 32-bit arithmetic throughout: N * L * P < 2^31 (checked by the launcher)
+  const unsigned uP = (unsigned)P, uL = (unsigned)L, S = (unsigned)N * uL, tn = (unsigned)tile_n;
+  const unsigned b = idx / uP, i = idx - b * uP;
+  const unsigned s = (i * S) / uP, e = ((i + 1u) * S + uP - 1u) / uP;
+  float sum = 0.0f;
+  const unsigned k0 = s / uL, k1 = (e - 1u) / uL;
+  for (unsigned k = k0; k <= k1; ++k) {
+    const unsigned na = max(s, k * uL) - k * uL, nb = min(e, (k + 1u) * uL) - k * uL;
+    for (unsigned t = na / tn; t <= (nb - 1u) / tn; ++t) {
+      const unsigned slot = i - ((k * uL + t * tn) * uP) / S;
+      if (slot <= 1u) sum += partial[(((size_t)b * N + k) * tiles + t) * 2 + slot];
+    }
+  }
+  feat[idx] = sum / (float)(e - s);
 }
 
 // Any (N, K): one thread per output, taps from global memory.  Correct for shapes without a specialised kernel.
@@ -509,16 +602,29 @@ __global__ void k_pqmf_synthesis_generic(const float* __restrict__ z, const floa
 template <int N, int K, int Q>
 int launch_analysis(const float* x, const float* H_host, const float* proto_host, const float* mod_host,
                     const float* row_scale, const float* mean_host, const float* std_host, float* out, int B, int T,
-                    int L, cudaStream_t st) {
+                    int L, cudaStream_t st, const PoolReq* pr = nullptr) {
   constexpr int TILE_N = PQ_THREADS * Q;
   const int tiles = (L + TILE_N - 1) / TILE_N;
   const unsigned grid = (unsigned)((size_t)B * tiles);
+  PoolArgs pool{nullptr, 0, 0};
+  if (pr) {
+    const long long S = (long long)N * L;
+    IAS_REQUIRE(pr->P > 0 && S * pr->P < (1LL << 31) && TILE_N + 1 <= S / pr->P, IAS_ERR_UNSUPPORTED,
+                "ias_pqmf_analysis_pooled: P=%d needs bins wider than the %d-step CTA tile (N*L=%lld)", pr->P, TILE_N, S);
+    const size_t need = (size_t)B * N * tiles * 2 * sizeof(float);
+    IAS_REQUIRE(pr->workspace && pr->workspace_bytes >= need, IAS_ERR_INVALID,
+                "ias_pqmf_analysis_pooled: workspace %zu < %zu bytes", pr->workspace_bytes, need);
+    pool.partial = static_cast<float*>(pr->workspace);
+    pool.P = pr->P;
+    pool.S = (int)S;
+  }
   BandNorm<N> norm;
   norm.on = (mean_host && std_host) ? 1 : 0;
   for (int k = 0; k < N; ++k) {
     norm.mean[k] = norm.on ? mean_host[k] : 0.0f;
     norm.std[k] = norm.on ? std_host[k] : 1.0f;
   }
+  {
   ProfScope prof_(K_PQMF_ANALYSIS, st);
   if (proto_host && mod_host) {
     TapsCM<N, K> taps;
@@ -532,13 +638,25 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
     } else {
       for (int i = 0; i < N * 2 * N; ++i) taps.c[i] = mod_host[i];
     }
-    k_pqmf_analysis<N, K, Q, TapsCM<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm);
+    if (pr)
+      k_pqmf_analysis<N, K, Q, TapsCM<N, K>, true><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm, pool);
+    else
+      k_pqmf_analysis<N, K, Q, TapsCM<N, K>, false><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm, pool);
   } else {
     Taps<N, K> taps;
     for (int i = 0; i < N * K; ++i) taps.h[i] = H_host[i];
-    k_pqmf_analysis<N, K, Q, Taps<N, K>><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm);
+    if (pr)
+      k_pqmf_analysis<N, K, Q, Taps<N, K>, true><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm, pool);
+    else
+      k_pqmf_analysis<N, K, Q, Taps<N, K>, false><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm, pool);
+  }
   }
   IAS_LAUNCH_CHECK("k_pqmf_analysis");
+  if (pr) {
+    ProfScope prof2_(K_POOL_FINALIZE, st);
+    k_pool_finalize<<<(B * pr->P + 255) / 256, 256, 0, st>>>(pool.partial, pr->feat, B, N, L, tiles, TILE_N, pr->P);
+    IAS_LAUNCH_CHECK("k_pool_finalize");
+  }
   return IAS_OK;
 }
 
@@ -589,7 +707,8 @@ extern "C" int ias_pqmf_out_len(int T, int N, int K) {
 namespace {
 int analysis_entry(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
                    const float* mod_host, const float* row_scale, const float* mean_host, const float* std_host,
-                   const float* norm_dev, float* out, int B, int T, int N, int K, ias_stream_t stream, const char* who) {
+                   const float* norm_dev, float* out, int B, int T, int N, int K, ias_stream_t stream, const char* who,
+                   const PoolReq* pr = nullptr) {
   IAS_REQUIRE(B > 0 && T > 0 && N > 0 && K > 0, IAS_ERR_INVALID, "%s: B=%d T=%d N=%d K=%d", who, B, T, N, K);
   IAS_REQUIRE(x && out, IAS_ERR_INVALID, "%s: NULL pointer", who);
   IAS_REQUIRE(H_dev || H_host, IAS_ERR_INVALID, "%s: no filter given", who);
@@ -598,7 +717,7 @@ int analysis_entry(const float* x, const float* H_dev, const float* H_host, cons
   cudaStream_t st = as_stream(stream);
   if (H_host && K == 63) {
 #define IAS_PQ(NN, QQ) \
-  case NN: return launch_analysis<NN, 63, QQ>(x, H_host, proto_host, mod_host, row_scale, mean_host, std_host, out, B, T, L, st);
+  case NN: return launch_analysis<NN, 63, QQ>(x, H_host, proto_host, mod_host, row_scale, mean_host, std_host, out, B, T, L, st, pr);
     switch (N) {
       IAS_PQ(2, 8)
       IAS_PQ(3, 4)  // measured (1024 x 4 s): Q=4 0.288 ms, Q=8 0.304 ms
@@ -609,6 +728,7 @@ int analysis_entry(const float* x, const float* H_dev, const float* H_host, cons
     }
 #undef IAS_PQ
   }
+  IAS_REQUIRE(!pr, IAS_ERR_UNSUPPORTED, "%s: N=%d K=%d has no specialised kernel (pooled epilogue unavailable)", who, N, K);
   IAS_REQUIRE(H_dev, IAS_ERR_UNSUPPORTED, "%s: N=%d K=%d has no specialised kernel and H_dev is NULL", who, N, K);
   IAS_REQUIRE(!(mean_host && std_host) || norm_dev, IAS_ERR_UNSUPPORTED,
               "%s: N=%d K=%d has no specialised kernel: the band normalisation needs norm_dev", who, N, K);
@@ -639,6 +759,24 @@ extern "C" int ias_pqmf_analysis_image(const float* x, const float* H_dev, const
     IAS_REQUIRE(std_host[k] != 0.0f, IAS_ERR_INVALID, "ias_pqmf_analysis_image: std[%d] == 0", k);
   return analysis_entry(x, H_dev, H_host, proto_host, mod_host, row_scale, mean_host, std_host, norm_dev, out, B, T, N,
                         K, stream, "ias_pqmf_analysis_image");
+}
+
+extern "C" size_t ias_pqmf_pool_workspace_bytes(int B, int T, int N, int K) {
+  const int L = ias_pqmf_out_len(T, N, K);
+  if (B <= 0 || L <= 0) return 0;
+  // tiles of the smallest CTA tile any specialised kernel uses (PQ_THREADS * 2 steps): an upper bound
+  const size_t tiles = ((size_t)L + 2 * PQ_THREADS - 1) / (2 * PQ_THREADS);
+  return (size_t)B * N * tiles * 2 * sizeof(float);
+}
+
+extern "C" int ias_pqmf_analysis_pooled(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
+                                        const float* mod_host, const float* row_scale, float* out, float* feat, int P,
+                                        void* workspace, size_t workspace_bytes, int B, int T, int N, int K,
+                                        ias_stream_t stream) {
+  IAS_REQUIRE(feat && workspace, IAS_ERR_INVALID, "ias_pqmf_analysis_pooled: NULL feat / workspace");
+  PoolReq pr{feat, P, workspace, workspace_bytes};
+  return analysis_entry(x, H_dev, H_host, proto_host, mod_host, row_scale, nullptr, nullptr, nullptr, out, B, T, N, K,
+                        stream, "ias_pqmf_analysis_pooled", &pr);
 }
 
 extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, const float* proto_host,

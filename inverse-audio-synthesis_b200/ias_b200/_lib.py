@@ -91,6 +91,9 @@ _SIGNATURES = {
     ),
     "ias_vicreg_gram_reference": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ias_vicreg_gram_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ias_pqmf_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "ias_pqmf_analysis_pooled": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p]),
     "ias_abs_avg_pool": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_longlong, c_int, c_void_p]),
 }
 

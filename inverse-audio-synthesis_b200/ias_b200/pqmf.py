@@ -137,6 +137,35 @@ class PQMF(nn.Module):
         _lib.check(rc, "ias_pqmf_analysis")
         return out
 
+    def analysis_pooled(self, x: torch.Tensor, bins: int, row_scale: Optional[torch.Tensor] = None):
+        """``analysis(x)`` plus ``adaptive_avg_pool1d(bands.abs().reshape(B, 1, -1), bins)`` computed by the same kernel
+        (the harness bridge between the bands and the embeddings; not a reference surface) -> (bands
+        [B,N,L], feat [B,bins]).  Raises ``IasError`` when the shape has no fused path; pool separately then."""
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise ValueError(f"PQMF.analysis_pooled expects [B,1,T], got {tuple(x.shape)}")
+        _lib.require_cuda(x, "PQMF.analysis_pooled input")
+        x = x.detach().to(torch.float32).contiguous()
+        B, _, T = x.shape
+        dev, host, factors = self._taps("H")
+        proto, mod = factors if (factors is not None and self.polyphase) else (None, None)
+        K = host.shape[1]
+        lib = _lib.lib()
+        L = lib.ias_pqmf_out_len(T, self.N, K)
+        if L <= 0:
+            raise ValueError(f"PQMF.analysis_pooled: input too short (T={T})")
+        out = torch.empty((B, self.N, L), dtype=torch.float32, device=x.device)
+        feat = torch.empty((B, bins), dtype=torch.float32, device=x.device)
+        nbytes = lib.ias_pqmf_pool_workspace_bytes(B, T, self.N, K)
+        ws = torch.empty((max(nbytes, 4) + 3) // 4, dtype=torch.float32, device=x.device)
+        if row_scale is not None:
+            row_scale = row_scale.detach().to(torch.float32).contiguous()
+        with _lib.on_device(x):
+            rc = lib.ias_pqmf_analysis_pooled(_lib.ptr(x), _lib.ptr(dev), _lib.ptr(host), _lib.ptr(proto), _lib.ptr(mod),
+                                              _lib.ptr(row_scale), _lib.ptr(out), _lib.ptr(feat), bins, _lib.ptr(ws),
+                                              ws.numel() * 4, B, T, self.N, K, _lib.current_stream(x.device))
+        _lib.check(rc, "ias_pqmf_analysis_pooled")
+        return out, feat
+
     def synthesis(self, x: torch.Tensor) -> torch.Tensor:
         """z [B,N,L] -> [B,1,L*N]  (pqmf.py:52-55)."""
         if x.dim() != 3 or x.shape[1] != self.N:

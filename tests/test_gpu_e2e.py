@@ -25,9 +25,15 @@ def test_front_end_step_vs_oracle(cuda_device):
     bands = gram(audio.unsqueeze(1))
     assert bands.shape == (B, 3, 58800)
     x, y = harness.bridge(bands, params, wa, wp)
+    # the bench's step pools inside the analysis kernel: same bands bit for bit, same embeddings to fp32 rounding
+    bands_f, x_f, y_f = harness.analysis_bridge(gram, audio, params, wa, wp)
+    assert torch.equal(bands_f, bands) and torch.equal(y_f, y)
+    assert float((x_f - x).abs().max() / x.abs().max()) <= 1e-5
     with torch.no_grad():
         out = vic.loss(x, y)
+        out_f = vic.loss(x_f, y_f)
     got = np.array([float(o) for o in out])
+    assert np.all(np.abs(np.array([float(o) for o in out_f]) - got) <= 1e-4 * np.abs(got))
     ref = harness.oracle_front_end(0, B, N=3)
     want = np.array(ref["loss4"])
     rel = np.abs(got - want) / np.abs(want)
@@ -88,8 +94,7 @@ def test_device_batch_index_and_cuda_graph_replay(cuda_device):
 
     def step(idx):
         audio, params, is_train = voice(idx)
-        bands = gram(audio.unsqueeze(1))
-        x, y = harness.bridge(bands, params, wa, wp)
+        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
         with torch.no_grad():
             return audio, params, is_train, torch.stack(vic.loss(x, y))
 

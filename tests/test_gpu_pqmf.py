@@ -192,3 +192,45 @@ def test_image_epilogue_matches_reshape_plus_normalize(cuda_device):
     assert torch.equal(m5.analysis_image(x5, mean5, std5), want5)
     with pytest.raises(ValueError):
         m.analysis_image(x, mean[:2], std[:2])
+
+
+@pytest.mark.parametrize("N,B,T,P", [(3, 5, 176400, 256), (16, 3, 176400, 256), (3, 2, 100003, 64), (8, 2, 44100, 16),
+                                       (3, 1024, 176400, 256)])
+def test_pooled_epilogue_matches_pooling_the_bands(cuda_device, N, B, T, P):
+    """Harness bridge: adaptive_avg_pool1d(|bands|.reshape(B,1,N*L), P) fused into the analysis kernel.
+    Bands are bit-identical to the unfused call; features agree with torch's pooling of those bands (fp32 sums in a
+    different order: 1e-5 relative) and are reproducible run to run."""
+    import harness
+
+    m = _mod(N, 0.15, cuda_device)
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + P)
+    x = (torch.rand((B, 1, T), generator=g) * 2 - 1).to(cuda_device)
+    x[0, 0, : T // 3] = 0.0  # a silent stretch: bins that are exactly zero
+    z = m(x)
+    z2, feat = m.analysis_pooled(x, P)
+    assert torch.equal(z, z2)
+    rows = slice(0, min(B, 16))
+    want = torch.nn.functional.adaptive_avg_pool1d(z[rows].double().abs().reshape(z[rows].shape[0], 1, -1).cpu(), P).squeeze(1)
+    got = feat[rows].double().cpu()
+    assert float((got - want).abs().max() / want.abs().max()) <= TOL
+    _, feat_again = m.analysis_pooled(x, P)
+    assert torch.equal(feat, feat_again)
+    # the stand-alone pooling kernel of the harness agrees too
+    if P == harness.EMBED_DIM:
+        wa, wp = harness.bridge_weights(cuda_device)
+        params = torch.zeros((B, harness.NPARAMS), device=cuda_device)
+        xa, _ = harness.bridge(z, params, wa, wp)
+        _, xb, _ = harness.analysis_bridge(m, x, params, wa, wp)
+        assert float((xa - xb).abs().max() / xa.abs().max()) <= TOL
+
+
+def test_pooled_epilogue_refuses_shapes_it_cannot_cover(cuda_device):
+    import ias_b200
+
+    m4 = _mod(4, 0.15, cuda_device)  # 1024-step CTA tiles: wider than a 689-element bin
+    x = MG.pqmf_input(1, 176400).to(cuda_device)
+    with pytest.raises(ias_b200.IasError):
+        m4.analysis_pooled(x, 256)
+    m5 = _mod(5, 0.15, cuda_device)  # no specialised kernel
+    with pytest.raises(ias_b200.IasError):
+        m5.analysis_pooled(x, 16)
