@@ -51,6 +51,24 @@ struct FoldCM {
 };
 constexpr int FOLD_MIN_N = 8;
 
+// A thread's run of CNT consecutive output floats (CNT % 4 == 0, 16-byte aligned): 256-bit stores (sm_100
+// st.global.v8.f32 -> STG.E.256) where the run is 32-byte aligned, so each store fills whole 32-byte sectors even
+// though the lanes of a warp are CNT floats apart; 128-bit stores otherwise.
+template <int CNT>
+__device__ __forceinline__ void store_run(float* __restrict__ dst, const float (&v)[CNT], bool wide) {
+  static_assert(CNT % 4 == 0, "run length");
+  if (CNT % 8 == 0 && wide) {
+#pragma unroll
+    for (int c = 0; c + 8 <= CNT; c += 8)
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c), "f"(v[c]), "f"(v[c + 1]),
+                   "f"(v[c + 2]), "f"(v[c + 3]), "f"(v[c + 4]), "f"(v[c + 5]), "f"(v[c + 6]), "f"(v[c + 7])
+                   : "memory");
+  } else {
+#pragma unroll
+    for (int c = 0; c < CNT; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  }
+}
+
 // Optional per-band epilogue (band - mean[k]) / std[k]: torchvision.transforms.Normalize on the [B,3,240,245] image
 // view the reference takes of the bands (audioembed.py:41,49; constants vicreg_audio_params.py:60-62).
 template <int N>
@@ -456,9 +474,7 @@ k_pqmf_synthesis(const float* __restrict__ z, float* __restrict__ y, int L, int 
     for (int q = 0; q < Q; ++q)
 #pragma unroll
       for (int p = 0; p < N; ++p) flat[q * N + p] = acc[q][p];
-#pragma unroll
-    for (int c = 0; c < Q * N; c += 4)
-      *reinterpret_cast<float4*>(yo + c) = make_float4(flat[c], flat[c + 1], flat[c + 2], flat[c + 3]);
+    store_run<Q * N>(yo, flat, (reinterpret_cast<uintptr_t>(yo) & 31u) == 0);
   } else {
 #pragma unroll
     for (int q = 0; q < Q; ++q)
@@ -571,11 +587,151 @@ k_pqmf_synthesis_cm(const float* __restrict__ z, float* __restrict__ y, int L, i
   }
   float* yo = y + (size_t)b * L * N + (size_t)n0 * N;
   if ((reinterpret_cast<uintptr_t>(y) & 15u) == 0 && (((size_t)L * N) % 4 == 0)) {
-#pragma unroll
-    for (int p = 0; p < N; p += 4) *reinterpret_cast<float4*>(yo + p) = make_float4(acc[p], acc[p + 1], acc[p + 2], acc[p + 3]);
+    store_run<N>(yo, acc, (reinterpret_cast<uintptr_t>(yo) & 31u) == 0);
   } else {
 #pragma unroll
     for (int p = 0; p < N; ++p) yo[p] = acc[p];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// synthesis, cosine-modulated form for small N (2, 3, 4): same factorisation as above with the N -> 2N modulation
+// done directly (2 N^2 multiply-adds per time step), and Q consecutive time steps per thread in the FIR phase so
+// that each modulated row read from shared memory serves Q time steps.  The N taps that meet one (time step, row)
+// pair are consecutive, and their residues j mod 2N alternate between two fixed halves of the row as the offset
+// advances; the row is stored as those two halves, each padded to 4 floats, so a (row, half) operand set is one
+// 128-bit shared load.  16 bytes of padding after every Q rows make both the phase-1 stores (one row per thread)
+// and the phase-2 loads (thread stride Q rows) conflict free.  63 + 2 N^2 instead of 63 N multiply-adds per step.
+// ------------------------------------------------------------------------------------------------------------
+template <int N, int K>
+struct TapsSynSmall {
+  float g[K];
+  float c[N * 2 * N];  // N cos(theta_k (r - (K-2)/2) - (-1)^k pi/4), [k][r]
+};
+
+template <int N, int K>
+struct SynRows {
+  using Geo = SynthGeom<N, K>;
+  static constexpr int PAD = (K - 1) / 2;
+  static constexpr int DMIN = Geo::omin();
+  static constexpr int HALO = Geo::omax() - DMIN;
+  static constexpr int N4 = (N + 3) / 4 * 4;
+  static constexpr int PITCH = 2 * N4;
+  // first tap of the block that meets offset o (may be negative / beyond K-1 at the ends)
+  __host__ __device__ static constexpr int jb(int o) { return PAD + N * (o - 1) + 1; }
+  __host__ __device__ static constexpr int ra() { return ((jb(DMIN) % (2 * N)) + 2 * N) % (2 * N); }
+  // residue stored at (half h, element e) of a row
+  __host__ __device__ static constexpr int res(int h, int e) { return (ra() + h * N + e) % (2 * N); }
+};
+
+template <int N, int K, int Q>
+__global__ void __launch_bounds__(PQ_THREADS)
+k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L, int tiles_per_row,
+                       TapsSynSmall<N, K> taps) {
+  using R = SynRows<N, K>;
+  constexpr int DMIN = R::DMIN, HALO = R::HALO, N4 = R::N4, PITCH = R::PITCH;
+  constexpr int TILE_N = PQ_THREADS * Q;
+  constexpr int ROWS = TILE_N + HALO;
+  constexpr int PASSES = (ROWS + PQ_THREADS - 1) / PQ_THREADS;
+  static_assert((Q * PITCH / 4) % 2 == 0, "padding scheme assumes an even number of 16-byte units per Q rows");
+  __shared__ __align__(16) float vs[ROWS * PITCH + (ROWS / Q + 1) * 4];
+
+  const int b = blockIdx.x / tiles_per_row;
+  const int tile = blockIdx.x - b * tiles_per_row;
+  const int n_tile = tile * TILE_N;
+  const float* zb = z + (size_t)b * N * L;
+
+  // ---- phase 1: modulate rows n_tile + DMIN + [0, ROWS) ----
+  float zk[PASSES][N];
+#pragma unroll
+  for (int i = 0; i < PASSES; ++i) {
+    const int row = (int)threadIdx.x + i * PQ_THREADS;
+    const int m = n_tile + DMIN + row;
+    const bool in = row < ROWS && m >= 0 && m < L;
+#pragma unroll
+    for (int k = 0; k < N; ++k) zk[i][k] = in ? __ldg(zb + (size_t)k * L + m) : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < PASSES; ++i) {
+    const int row = (int)threadIdx.x + i * PQ_THREADS;
+    if (row < ROWS) {
+      float* dst = vs + row * PITCH + (row / Q) * 4;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[N4];
+#pragma unroll
+        for (int e = 0; e < N4; ++e) {
+          v[e] = 0.0f;
+          if (e < N) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) v[e] = fmaf(taps.c[k * 2 * N + R::res(h, e)], zk[i][k], v[e]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < N4; e += 4)
+          *reinterpret_cast<float4*>(dst + h * N4 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: Q time steps per thread, rows streamed once ----
+  const int n0 = n_tile + (int)threadIdx.x * Q;
+  if (n0 >= L) return;
+  float acc[Q][N];
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+#pragma unroll
+    for (int p = 0; p < N; ++p) acc[q][p] = 0.0f;
+  const float* base = vs + (int)threadIdx.x * (Q * PITCH + 4);  // row threadIdx.x * Q
+#pragma unroll
+  for (int i = 0; i < Q + HALO; ++i) {
+    const float* row = base + i * PITCH + (i / Q) * 4;
+    float w[2][N4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // half h of this row is used by the time steps q with offset o = DMIN + i - q in range and (i - q) parity h
+      bool need = false;
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (i - q >= 0 && i - q <= HALO && ((i - q) & 1) == h) need = true;
+      if (need) {
+#pragma unroll
+        for (int e = 0; e < N4; e += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(row + h * N4 + e);
+          w[h][e] = t.x; w[h][e + 1] = t.y; w[h][e + 2] = t.z; w[h][e + 3] = t.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int d = i - q;  // o - DMIN
+      if (d >= 0 && d <= HALO) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const int j = R::jb(DMIN + d) + e;
+          if (j >= 0 && j < K) acc[q][R::Geo::phase(j)] = fmaf(taps.g[j], w[d & 1][e], acc[q][R::Geo::phase(j)]);
+        }
+      }
+    }
+  }
+
+  float* yo = y + (size_t)b * L * N + (size_t)n0 * N;
+  const bool st_vec = (((size_t)L * N) % 4 == 0) && ((Q * N) % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+  if (st_vec && n0 + Q <= L) {
+    float flat[Q * N];
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int p = 0; p < N; ++p) flat[q * N + p] = acc[q][p];
+    store_run<Q * N>(yo, flat, (reinterpret_cast<uintptr_t>(yo) & 31u) == 0);
+  } else {
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+      if (n0 + q < L) {
+#pragma unroll
+        for (int p = 0; p < N; ++p) yo[q * N + p] = acc[q][p];
+      }
   }
 }
 
@@ -692,6 +848,24 @@ int launch_synthesis_cm(const float* z, const float* proto_host, float* y, int B
   return IAS_OK;
 }
 
+template <int N, int K, int Q>
+int launch_synthesis_small(const float* z, const float* proto_host, float* y, int B, int L, cudaStream_t st) {
+  TapsSynSmall<N, K> taps;
+  for (int i = 0; i < K; ++i) taps.g[i] = proto_host[i];
+  for (int k = 0; k < N; ++k)
+    for (int r = 0; r < 2 * N; ++r)
+      taps.c[k * 2 * N + r] = (float)(N * cos((2.0 * k + 1.0) * (3.14159265358979323846 / (2.0 * N)) * (r - (K - 2) / 2.0) -
+                                              ((k & 1) ? -1.0 : 1.0) * 3.14159265358979323846 / 4.0));
+  constexpr int TILE_N = PQ_THREADS * Q;
+  const int tiles = (L + TILE_N - 1) / TILE_N;
+  {
+    ProfScope prof_(K_PQMF_SYNTHESIS, st);
+    k_pqmf_synthesis_small<N, K, Q><<<(unsigned)((size_t)B * tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_synthesis_small");
+  return IAS_OK;
+}
+
 }  // namespace
 }  // namespace ias
 
@@ -785,9 +959,22 @@ extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const floa
   IAS_REQUIRE(z && y, IAS_ERR_INVALID, "ias_pqmf_synthesis: NULL pointer");
   IAS_REQUIRE(G_dev || G_host, IAS_ERR_INVALID, "ias_pqmf_synthesis: no filter given");
   cudaStream_t st = as_stream(stream);
+  int q_env = 0;  // IAS_PQMF_SYNTH_Q: tuning override of the time steps per thread
+  if (const char* e = getenv("IAS_PQMF_SYNTH_Q")) q_env = atoi(e);
   if (proto_host && K == 63) {  // G is the designed filter: cosine-modulated form
     if (N == 16) return launch_synthesis_cm<16, 63>(z, proto_host, y, B, L, st);
     if (N == 8) return launch_synthesis_cm<8, 63>(z, proto_host, y, B, L, st);
+    if (!getenv("IAS_PQMF_SYNTH_DIRECT")) {  // tuning switch: direct form for N <= 4
+      if (N == 4) {
+        if (q_env == 8) return launch_synthesis_small<4, 63, 8>(z, proto_host, y, B, L, st);
+        return launch_synthesis_small<4, 63, 4>(z, proto_host, y, B, L, st);  // measured: Q=4 0.411 ms, Q=8 0.471, direct 0.643
+      }
+      if (N == 3) {
+        if (q_env == 4) return launch_synthesis_small<3, 63, 4>(z, proto_host, y, B, L, st);
+        return launch_synthesis_small<3, 63, 8>(z, proto_host, y, B, L, st);  // measured: Q=8 0.439 ms, Q=4 0.485, direct 0.494
+      }
+      if (N == 2) return launch_synthesis_small<2, 63, 4>(z, proto_host, y, B, L, st);
+    }
   }
   if (G_host && K == 63) {
     int q = 0;  // IAS_PQMF_SYNTH_Q: tuning override of the time steps per thread
