@@ -241,7 +241,7 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
 #pragma unroll
       for (int k = 0; k < N; ++k)
 #pragma unroll
-        for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.h[k * K + j], w[q * N + j], acc[q][k]);
+        for (int q = 0; q < Q; ++q) acc[q][k] = fmaf(taps.h[j * N + k], w[q * N + j], acc[q][k]);  // tap-major copy
   } else {
     // polyphase form: fold the 63 taps into 2N partial sums shared by all bands (63 FMA per time step), then the
     // N x 2N cosine modulation (2N*N FMA per time step): 63 + 2N^2 instead of 63N
@@ -270,7 +270,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
         for (int m = 0; m < N; ++m) {
           const float v = sum[m] - dif[N - 1 - m];
 #pragma unroll
-          for (int k = 0; k < N; ++k) acc[q][k] = fmaf(taps.c[k * N + m], v, acc[q][k]);
+          for (int k = 0; k < N; ++k) acc[q][k] = fmaf(taps.c[m * N + k], v, acc[q][k]);  // C is symmetric: row m is
+                                                                                          // contiguous -> LDCU.128
         }
       }
     } else {
@@ -799,8 +800,9 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
     else
       k_pqmf_analysis<N, K, Q, TapsCM<N, K>, false><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm, pool);
   } else {
-    Taps<N, K> taps;
-    for (int i = 0; i < N * K; ++i) taps.h[i] = H_host[i];
+    Taps<N, K> taps;  // tap-major ([j][k]) so the bands of one tap are contiguous constants (vectorised LDCU)
+    for (int k = 0; k < N; ++k)
+      for (int j = 0; j < K; ++j) taps.h[j * N + k] = H_host[k * K + j];
     if (pr)
       k_pqmf_analysis<N, K, Q, Taps<N, K>, true><<<grid, PQ_THREADS, 0, st>>>(x, row_scale, out, T, L, tiles, taps, norm, pool);
     else
