@@ -98,6 +98,17 @@ IAS_API int ias_voice_render(const float* params01, const float* noise, int nois
                      const float* ctrl_in, float* phase_dbg, void* workspace, size_t workspace_bytes,
                      ias_stream_t stream);
 
+/* The same call split in two, so that a caller can overlap the (latency-bound) control stage of the NEXT batch with
+ * whatever consumes the current audio: IAS_VOICE_STAGE_CONTROL runs ADSR + LFO/modulation + the work-queue schedule
+ * from params01 into `workspace` (noise / audio / peak may be NULL); IAS_VOICE_STAGE_AUDIO renders the audio from a
+ * workspace a control-stage call filled (params01 / ctrl_in unused).  Both bits = ias_voice_render. */
+#define IAS_VOICE_STAGE_CONTROL 1
+#define IAS_VOICE_STAGE_AUDIO 2
+IAS_API int ias_voice_render_stages(const float* params01, const float* noise, int noise_rows, float* audio, float* peak,
+                            int B, int T, int C, float sample_rate, float control_rate, float eps, int normalize,
+                            const float* ctrl_in, float* phase_dbg, void* workspace, size_t workspace_bytes, int stages,
+                            ias_stream_t stream);
+
 /* ---- PQMF: pqmf.PQMF (pqmf.py:9-55; callers audioembed.py:38, vicreg_audio_params.py:40) ----------------- */
 
 /* Output length of analysis: floor((T + 2*((K-1)/2) - K) / N) + 1 with K = taps + 1 (pqmf.py:49-50). */

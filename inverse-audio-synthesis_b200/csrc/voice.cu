@@ -908,15 +908,16 @@ AudioShape pick_shape(int T) {
   return s;
 }
 
-int launch_audio(const AudioArgs& a, const VoiceWorkspace& w, bool dbg, cudaStream_t st) {
+int launch_audio(const AudioArgs& a, const VoiceWorkspace& w, bool dbg, bool schedule, bool audio, cudaStream_t st) {
   const AudioShape s = pick_shape(a.T);
   const bool vec = (a.T % s.spt == 0) && ias_aligned16(a.noise) && ias_aligned16(a.audio);
-  {
+  if (schedule) {
     ProfScope prof_(K_VOICE_SCHEDULE, st);
     k_voice_schedule<<<1, SCHED_THREADS, 0, st>>>(a.vconst, a.B, a.T, a.scale, s.nt * s.spt, dbg ? 1 : 0, w.ntiles,
                                                   w.order, w.counter);
   }
   IAS_LAUNCH_CHECK("k_voice_schedule");
+  if (!audio) return IAS_OK;
 #define IAS_SHAPE(NT, SPT, MINB) \
   if (s.nt == NT && s.spt == SPT && s.ctas_per_sm == MINB) { launch_audio_shape<NT, SPT, MINB>(a, vec, dbg, st); } else
   IAS_SHAPE(128, 8, 7)
@@ -1002,20 +1003,37 @@ extern "C" int ias_voice_render(const float* params01, const float* noise, int n
                                 int B, int T, int C, float sample_rate, float control_rate, float eps, int normalize,
                                 const float* ctrl_in, float* phase_dbg, void* workspace, size_t workspace_bytes,
                                 ias_stream_t stream) {
+  return ias_voice_render_stages(params01, noise, noise_rows, audio, peak, B, T, C, sample_rate, control_rate, eps,
+                                 normalize, ctrl_in, phase_dbg, workspace, workspace_bytes,
+                                 IAS_VOICE_STAGE_CONTROL | IAS_VOICE_STAGE_AUDIO, stream);
+}
+
+extern "C" int ias_voice_render_stages(const float* params01, const float* noise, int noise_rows, float* audio,
+                                       float* peak, int B, int T, int C, float sample_rate, float control_rate,
+                                       float eps, int normalize, const float* ctrl_in, float* phase_dbg,
+                                       void* workspace, size_t workspace_bytes, int stages, ias_stream_t stream) {
+  const bool do_control = (stages & IAS_VOICE_STAGE_CONTROL) != 0, do_audio = (stages & IAS_VOICE_STAGE_AUDIO) != 0;
+  IAS_REQUIRE(do_control || do_audio, IAS_ERR_INVALID, "ias_voice_render: stages=%d selects nothing", stages);
+  if (!do_audio) {  // control stage only: the audio-side pointers are not used
+    noise_rows = noise_rows > 0 ? noise_rows : 1;
+  }
   IAS_REQUIRE(B > 0 && T > 1 && C > 1 && noise_rows > 0, IAS_ERR_INVALID, "ias_voice_render: B=%d T=%d C=%d R=%d", B,
               T, C, noise_rows);
   IAS_REQUIRE(T < (1 << 24), IAS_ERR_UNSUPPORTED, "ias_voice_render: T=%d exceeds 2^24 samples", T);
   IAS_REQUIRE((long long)(T - 1) >= 16ll * (C - 1), IAS_ERR_UNSUPPORTED,
               "ias_voice_render: needs at least %d audio samples per control sample (T=%d C=%d)", 16, T, C);
-  IAS_REQUIRE(params01 && noise && audio, IAS_ERR_INVALID, "ias_voice_render: NULL pointer");
+  IAS_REQUIRE((!do_control || params01) && (!do_audio || (noise && audio)), IAS_ERR_INVALID,
+              "ias_voice_render: NULL pointer");
   IAS_REQUIRE(sample_rate > 0.f && control_rate > 0.f, IAS_ERR_INVALID, "ias_voice_render: rates must be positive");
   IAS_REQUIRE(workspace && workspace_bytes >= ias_voice_workspace_bytes(B, T, C), IAS_ERR_WORKSPACE,
               "ias_voice_render: workspace %zu < %zu bytes", workspace_bytes, ias_voice_workspace_bytes(B, T, C));
   IAS_REQUIRE(ias_aligned16(workspace), IAS_ERR_INVALID, "ias_voice_render: workspace must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   VoiceWorkspace w = carve(workspace, B, C);
-  int rc = launch_control(params01, B, C, control_rate, eps, ctrl_in, nullptr, w, st);
-  if (rc) return rc;
+  if (do_control) {
+    int rc = launch_control(params01, B, C, control_rate, eps, ctrl_in, nullptr, w, st);
+    if (rc) return rc;
+  }
   AudioArgs a;
   a.rec = w.rec;
   a.vconst = w.vconst;
@@ -1031,5 +1049,6 @@ extern "C" int ias_voice_render(const float* params01, const float* noise, int n
   a.sr = sample_rate;
   a.rsr = 1.0f / sample_rate;
   a.normalize = normalize;
-  return launch_audio(a, w, phase_dbg != nullptr, st);
+  // the work queue (k_voice_schedule) belongs to the control stage: it depends on the control signals only
+  return launch_audio(a, w, phase_dbg != nullptr, do_control, do_audio, st);
 }

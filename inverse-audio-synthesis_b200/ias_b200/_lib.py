@@ -60,6 +60,11 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_int,
          c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
+    "ias_voice_render_stages": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_int,
+         c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p],
+    ),
     "ias_pqmf_out_len": (c_int, [c_int, c_int, c_int]),
     "ias_pqmf_analysis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int, c_int, c_void_p]),

@@ -390,6 +390,38 @@ class Voice(nn.Module):
     def _frozen_rows(self) -> List[int]:
         return [1 if p.frozen else 0 for p in self._param_list()]
 
+    STAGE_CONTROL, STAGE_AUDIO = 1, 2
+
+    def prepare(self, batch_idx) -> None:
+        """Seed the parameters of batch ``batch_idx`` and run the control stage (envelopes, LFOs, modulation, work
+        queue) into the workspace, without rendering.  ``forward(batch_idx, prepared=True)`` then renders exactly that
+        batch with the audio stage alone.  A training loop knows its next batch number, so it can issue this on a side
+        stream while the current batch's audio is still being consumed (PQMF, backbone, loss): the control stage is
+        latency-bound and hides behind that work.  Not a torchsynth method."""
+        if batch_idx is None:
+            raise ValueError("Voice.prepare needs a batch index")
+        on_device = isinstance(batch_idx, torch.Tensor) and batch_idx.is_cuda
+        with torch.no_grad():
+            self.randomize(seed=batch_idx if on_device else int(batch_idx))
+            self._render(self.STAGE_CONTROL, None)
+        self._prepared = batch_idx if on_device else int(batch_idx)
+
+    def _render(self, stages: int, audio: Optional[torch.Tensor], phase_debug=None, ctrl_in=None):
+        cfg = self.synthconfig
+        _lib.require_cuda(self._store, "Voice parameters")
+        noise = self.noise.noise
+        _lib.require_cuda(noise, "Voice noise buffer")
+        if self._peak is None or self._peak.device != self.device:
+            self._peak = torch.empty(cfg.batch_size, dtype=torch.float32, device=self.device)
+        ws = self._ws()
+        with _lib.on_device(self._store):
+            rc = _lib.lib().ias_voice_render_stages(
+                _lib.ptr(self._store), _lib.ptr(noise), noise.shape[0], _lib.ptr(audio), _lib.ptr(self._peak),
+                cfg.batch_size, cfg.buffer_size, cfg.control_buffer_size, float(cfg.sample_rate),
+                float(cfg.control_rate), float(cfg.eps), 1 if self.normalize else 0, _lib.ptr(ctrl_in),
+                _lib.ptr(phase_debug), _lib.ptr(ws), ws.numel(), stages, _lib.current_stream(self.device))
+        _lib.check(rc, "ias_voice_render_stages")
+
     def output(self, return_peak: bool = False, phase_debug: Optional[torch.Tensor] = None,
                ctrl_in: Optional[torch.Tensor] = None, _tied: bool = False) -> torch.Tensor:
         """Voice.output(): render the current parameters to audio [B, T].  ``phase_debug`` / ``ctrl_in`` are the
@@ -433,13 +465,27 @@ class Voice(nn.Module):
         self._tie()
         return self._store.t().contiguous()
 
-    def forward(self, batch_idx=None):
+    def forward(self, batch_idx=None, prepared: bool = False):
         """-> (audio[B,T], params[B,78], is_train[B] or None)  (vicreg_audio_params.py:114).  ``batch_idx`` is an int
         (or anything ``int()`` accepts, as in the reference) or a one-element int64 CUDA tensor, which is read on the
-        device."""
+        device.  ``prepared=True``: ``prepare(batch_idx)`` already seeded this batch and ran its control stage; only the
+        audio stage runs (same result, bit for bit)."""
         if self.synthconfig.reproducible and batch_idx is None:
             raise ValueError("Reproducible mode is on, you must pass a batch index")
         ctx = torch.no_grad() if self.synthconfig.no_grad else torch.enable_grad()
+        if prepared:
+            want = getattr(self, "_prepared", None)
+            on_device = isinstance(batch_idx, torch.Tensor) and batch_idx.is_cuda
+            if want is None or (not on_device and not isinstance(want, torch.Tensor) and int(batch_idx) != want):
+                raise RuntimeError(f"Voice.forward(prepared=True): batch {batch_idx} was not prepared (have {want})")
+            self._prepared = None
+            with ctx:
+                is_train = self._is_train.bool()
+                params = self._store.t().contiguous()
+                cfg = self.synthconfig
+                audio = torch.empty((cfg.batch_size, cfg.buffer_size), dtype=torch.float32, device=self.device)
+                self._render(self.STAGE_AUDIO, audio)
+            return audio, params, is_train
         with ctx:
             if batch_idx is not None:
                 on_device = isinstance(batch_idx, torch.Tensor) and batch_idx.is_cuda

@@ -151,3 +151,86 @@ def test_second_device_in_the_same_process(cuda_device):
         outs.append((audio.cpu(), bands.cpu(), torch.stack([l.detach() for l in loss]).cpu(), x.grad.cpu()))
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+def test_prepared_batches_render_bit_identically(cuda_device):
+    """Voice.prepare(k+1) on a side stream while batch k is consumed, then Voice(k+1, prepared=True): the audio stage
+    alone renders exactly what Voice(k+1) renders (audio, parameters, is_train, loss), eagerly and from a CUDA graph."""
+    import ias_b200
+
+    B = 32
+    cfg = ias_b200.SynthConfig(batch_size=B, reproducible=True, sample_rate=44100, buffer_size_seconds=4.0)
+    voice = ias_b200.Voice(synthconfig=cfg).to(cuda_device)
+    gram = ias_b200.PQMF(N=3).to(cuda_device)
+    vcfg = types.SimpleNamespace(dim=256, embeddim=256, vicreg=types.SimpleNamespace(
+        mlp="8-8-%d", batch_size=B, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
+    vic = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity())
+    wa, wp = harness.bridge_weights(cuda_device)
+
+    def tail(audio, params):
+        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
+        with torch.no_grad():
+            return torch.stack(vic.loss(x, y))
+
+    batches = [4, 5, 6, 7]
+    want = []
+    for k in batches:
+        audio, params, is_train = voice(k)
+        want.append((audio.clone(), params.clone(), is_train.clone(), tail(audio, params).clone()))
+
+    side = torch.cuda.Stream(device=cuda_device)
+    voice.prepare(batches[0])
+    for n, k in enumerate(batches):
+        audio, params, is_train = voice(k, prepared=True)
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            voice.prepare(k + 1)
+        loss = tail(audio, params)
+        cur.wait_stream(side)
+        for got, ref in zip((audio, params, is_train, loss), want[n]):
+            assert torch.equal(got, ref)
+    # a batch that was not prepared is refused
+    voice.prepare(3)
+    with pytest.raises(RuntimeError):
+        voice(9, prepared=True)
+    audio3, _, _ = voice(3, prepared=True)  # the refused call left the prepared state alone
+    assert torch.equal(audio3, voice(3)[0])
+    with pytest.raises(RuntimeError):
+        voice(3, prepared=True)  # consumed
+
+    # the same pipeline captured in a CUDA graph with a device-resident batch number
+    idx = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+
+    def step():
+        audio, params, is_train = voice(idx, prepared=True)
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            idx.add_(1)
+            voice.prepare(idx)
+        loss = tail(audio, params)
+        cur.wait_stream(side)
+        return audio, params, is_train, loss
+
+    def prime():
+        idx.fill_(batches[0])
+        voice.prepare(idx)
+
+    prime()
+    warm = torch.cuda.Stream(device=cuda_device)
+    warm.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(warm):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(warm)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step()
+    prime()
+    for n in range(len(batches)):
+        g.replay()
+        torch.cuda.synchronize()
+        for got, ref in zip(out, want[n]):
+            assert torch.equal(got, ref)
