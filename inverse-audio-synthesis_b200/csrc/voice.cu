@@ -498,8 +498,9 @@ __device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
 // vm::vco_increment for two samples: 2*pi*hz(clamp(midi + depth*mod, 0, 127)) / sample_rate, same op order.
 template <bool CLAMP>
 __device__ __forceinline__ P2 vco_increment_p2(float midi, float depth, P2 mod, float sr, float rsr) {
-  // depth * mod in scalar form, so that the product keeps its own rounding (see the note on contraction above)
-  P2 m = p2_add(p2b(midi), p2(mul(depth, p2lo(mod)), mul(depth, p2hi(mod))));
+  // depth * mod must keep its own rounding (see the note on contraction above): issued as fma(depth, mod, +0.0),
+  // which ptxas can neither fold into a multiply (a -0 product would change sign) nor contract with the add
+  P2 m = p2_add(p2b(midi), p2_fma(p2b(depth), mod, p2b(0.0f)));
   if (CLAMP)  // voices whose range is provably inside (VC_NOCLAMP) skip the four min/max instructions
     m = p2(fminf(fmaxf(p2lo(m), 0.0f), 127.0f), fminf(fmaxf(p2hi(m), 0.0f), 127.0f));
   const P2 a = p2_add(m, p2b(-69.0f));
@@ -581,8 +582,9 @@ __device__ __forceinline__ void pitch_pass(float (&x1)[SPT], float (&x2)[SPT], f
 #pragma unroll
   for (int k = 0; k < SPT; k += 2) {
     const P2 fi = p2_add(p2b(ft0), p2((float)k, (float)(k + 1)));
-    // the reference's fp32 source coordinate; scalar products so that they are rounded before the subtraction
-    const float s0 = mul(scale, p2lo(fi)), s1 = mul(scale, p2hi(fi));
+    // the reference's fp32 source coordinate, rounded before the subtraction: fma(scale, i, +0.0), as above
+    const P2 sp = p2_fma(p2b(scale), fi, p2b(0.0f));
+    const float s0 = p2lo(sp), s1 = p2hi(sp);
     srcs[k] = s0;
     srcs[k + 1] = s1;
     const bool d0 = s0 >= fj1, d1 = s1 >= fj1;
