@@ -33,7 +33,29 @@ template <int N, int K>
 struct TapsCM {
   float g[K];
   float c[N * 2 * N];
+  // the prototype again, as the tap pairs the packed (FFMA2) polyphase stage multiplies two adjacent samples by:
+  // ge[m] = (g[2m], g[2m+1]) and go[m] = (g[2m-1], g[2m]), zero outside [0, K)
+  float2 ge[(K + 1) / 2];
+  float2 go[(K + 1) / 2];
 };
+
+// packed fp32 pair (sm_100 fma.rn.f32x2 -> FFMA2: two IEEE fp32 lanes per instruction, same rounding as scalar FFMA)
+struct P2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ P2 p2(float lo, float hi) {
+  P2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void p2_unpack(P2 a, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ P2 p2_fma(P2 a, P2 b, P2 c) {
+  P2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
 
 // For N >= 8 the N x 2N cosine modulation is evaluated as one size-N DCT-IV on folded partial sums.  With
 // t = r - (K-2)/2, every residue r maps to t' = t + 2N*q in {+-(m + 1/2)}, m < N, with sign (-1)^q (the cosine flips
@@ -163,6 +185,20 @@ __device__ __forceinline__ void stage_row_interior(float* __restrict__ dst, cons
     }
 }
 
+// The same window as raw 128-bit groups: wr[i] = staged float t*S + i for i < NRAW (NRAW % 4 == 0), so that callers
+// know which elements share an aligned register pair (i even).
+template <int S, int NRAW>
+__device__ __forceinline__ void load_window_raw(const float* __restrict__ src, float (&wr)[NRAW]) {
+  using P = Pad<S>;
+  static_assert(P::VEC && NRAW % 4 == 0, "raw windows need the 128-bit layout");
+  const float* base = src + threadIdx.x * P::SP;
+#pragma unroll
+  for (int i = 0; i < NRAW / 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(base + P::at(4 * i));
+    wr[4 * i] = v.x; wr[4 * i + 1] = v.y; wr[4 * i + 2] = v.z; wr[4 * i + 3] = v.w;
+  }
+}
+
 // Sliding window of this thread: linear floats [t*S + OFF, t*S + OFF + WIN) of the staged row -> registers.
 template <int S, int OFF, int WIN>
 __device__ __forceinline__ void load_window(const float* __restrict__ src, float (&w)[WIN]) {
@@ -227,8 +263,6 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   }
   __syncthreads();
 
-  float w[WIN];
-  load_window<S, OFF, WIN>(xs, w);
   float acc[Q][N];
 #pragma unroll
   for (int q = 0; q < Q; ++q)
@@ -236,6 +270,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
     for (int k = 0; k < N; ++k) acc[q][k] = 0.0f;
   if constexpr (std::is_same<TapsT, Taps<N, K>>::value) {
     // direct form: 63*N FMA per time step; valid for any H (e.g. loaded from a checkpoint)
+    float w[WIN];
+    load_window<S, OFF, WIN>(xs, w);
 #pragma unroll
     for (int j = 0; j < K; ++j)
 #pragma unroll
@@ -246,14 +282,56 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
     // polyphase form: fold the 63 taps into 2N partial sums shared by all bands (63 FMA per time step), then the
     // N x 2N cosine modulation (2N*N FMA per time step): 63 + 2N^2 instead of 63N
     float ps[Q][2 * N];
+    if constexpr (K % 2 == 1 && Pad<S>::VEC) {
+      // two adjacent taps per FFMA2: the kernel is issue bound, and the 63 prototype multiply-adds per time step are
+      // most of its instructions.  A pair needs its two samples in one aligned register pair, i.e. at an even raw
+      // index of the 128-bit window groups: steps whose first sample sits at an even index pair taps (0,1), (2,3),
+      // ..., steps at an odd index pair (-1,0), (1,2), ... (tap -1 and tap K are zero, their sample lane is a
+      // literal 0).  Each lane is the same fma chain, in the same tap order, as the scalar form.
+      constexpr int NRAW = (OFF + WIN + 3) / 4 * 4;
+      constexpr int NP = (K + 1) / 2;
+      float wr[NRAW];
+      load_window_raw<S, NRAW>(xs, wr);
 #pragma unroll
-    for (int q = 0; q < Q; ++q)
+      for (int q = 0; q < Q; ++q) {
+        const int base = q * N + OFF;  // raw index of the sample tap 0 multiplies (compile-time after unrolling)
+        P2 pp[N];
 #pragma unroll
-      for (int r = 0; r < 2 * N; ++r) ps[q][r] = 0.0f;
+        for (int i = 0; i < N; ++i) pp[i] = p2(0.0f, 0.0f);
+        if (base % 2 == 0) {
 #pragma unroll
-    for (int j = 0; j < K; ++j)
+          for (int m = 0; m < NP; ++m) {
+            const float2 t = taps.ge[m];
+            const P2 x = (2 * m + 1 < K) ? p2(wr[base + 2 * m], wr[base + 2 * m + 1]) : p2(wr[base + 2 * m], 0.0f);
+            const int i = ((2 * m) % (2 * N)) / 2;
+            pp[i] = p2_fma(p2(t.x, t.y), x, pp[i]);
+          }
 #pragma unroll
-      for (int q = 0; q < Q; ++q) ps[q][j % (2 * N)] = fmaf(taps.g[j], w[q * N + j], ps[q][j % (2 * N)]);
+          for (int i = 0; i < N; ++i) p2_unpack(pp[i], ps[q][2 * i], ps[q][2 * i + 1]);
+        } else {
+#pragma unroll
+          for (int m = 0; m < NP; ++m) {
+            const float2 t = taps.go[m];
+            const P2 x = (m > 0) ? p2(wr[base + 2 * m - 1], wr[base + 2 * m]) : p2(0.0f, wr[base]);
+            const int i = (((2 * m - 1) % (2 * N) + 2 * N) % (2 * N) - 1) / 2;  // lanes (2i+1, 2i+2 mod 2N)
+            pp[i] = p2_fma(p2(t.x, t.y), x, pp[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < N; ++i) p2_unpack(pp[i], ps[q][2 * i + 1], ps[q][(2 * i + 2) % (2 * N)]);
+        }
+      }
+    } else {
+      float w[WIN];
+      load_window<S, OFF, WIN>(xs, w);
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int r = 0; r < 2 * N; ++r) ps[q][r] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) ps[q][j % (2 * N)] = fmaf(taps.g[j], w[q * N + j], ps[q][j % (2 * N)]);
+    }
     if constexpr (N >= FOLD_MIN_N) {
       using F = FoldCM<N, K>;
 #pragma unroll
@@ -786,6 +864,11 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
   if (proto_host && mod_host) {
     TapsCM<N, K> taps;
     for (int i = 0; i < K; ++i) taps.g[i] = proto_host[i];
+    auto tap = [&](int j) { return (j >= 0 && j < K) ? proto_host[j] : 0.0f; };
+    for (int m = 0; m < (K + 1) / 2; ++m) {
+      taps.ge[m] = make_float2(tap(2 * m), tap(2 * m + 1));
+      taps.go[m] = make_float2(tap(2 * m - 1), tap(2 * m));
+    }
     if (N >= FOLD_MIN_N) {  // the folded form needs only N: cos((2k+1)(2m+1)pi/(4N)) / sqrt(2)
       for (int i = 0; i < N * 2 * N; ++i) taps.c[i] = 0.0f;
       for (int k = 0; k < N; ++k)
