@@ -31,7 +31,7 @@ struct Taps {
 // g[j] = (-1)^floor(j/2N) * 2*prototype[j] and c[k][r] = cos((2k+1)*pi/(2N) * (r - (taps-1)/2) + (-1)^k*pi/4).
 template <int N, int K>
 struct TapsCM {
-  float g[K];
+  float g[K + (K & 1)];  // padded so that c starts 8-byte aligned (read as float2 pairs by the packed stages)
   float c[N * 2 * N];
   // the prototype again, as the tap pairs the packed (FFMA2) polyphase stage multiplies two adjacent samples by:
   // ge[m] = (g[2m], g[2m+1]) and go[m] = (g[2m-1], g[2m]), zero outside [0, K)
@@ -344,13 +344,22 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
           sum[m] = pm + qm;
           dif[m] = pm - qm;
         }
+        // C is symmetric: row m is contiguous (vectorised constant loads); two bands per FFMA2
+        P2 ap[N / 2];
+#pragma unroll
+        for (int k2 = 0; k2 < N / 2; ++k2) ap[k2] = p2(0.0f, 0.0f);
 #pragma unroll
         for (int m = 0; m < N; ++m) {
           const float v = sum[m] - dif[N - 1 - m];
+          const P2 vv = p2(v, v);
 #pragma unroll
-          for (int k = 0; k < N; ++k) acc[q][k] = fmaf(taps.c[m * N + k], v, acc[q][k]);  // C is symmetric: row m is
-                                                                                          // contiguous -> LDCU.128
+          for (int k2 = 0; k2 < N / 2; ++k2) {
+            const float2 t = reinterpret_cast<const float2*>(taps.c)[(m * N) / 2 + k2];
+            ap[k2] = p2_fma(p2(t.x, t.y), vv, ap[k2]);
+          }
         }
+#pragma unroll
+        for (int k2 = 0; k2 < N / 2; ++k2) p2_unpack(ap[k2], acc[q][2 * k2], acc[q][2 * k2 + 1]);
       }
     } else {
 #pragma unroll
@@ -580,7 +589,7 @@ k_pqmf_synthesis(const float* __restrict__ z, float* __restrict__ y, int L, int 
 // ------------------------------------------------------------------------------------------------------------
 template <int N, int K>
 struct TapsSynCM {
-  float g[K];
+  float g[K + (K & 1)];  // padded so that c starts 8-byte aligned
   float c[N * N];  // (N / sqrt 2) cos((2k+1)(2m+1) pi / (4N)), [k][m]
 };
 
@@ -619,12 +628,22 @@ k_pqmf_synthesis_cm(const float* __restrict__ z, float* __restrict__ y, int L, i
 #pragma unroll
     for (int k = 0; k < N; ++k) zk[k] = in ? __ldg(zp + (size_t)k * L) : 0.0f;
     float u[N];
+    {
+      P2 up[N / 2];  // two DCT outputs per FFMA2
 #pragma unroll
-    for (int mm = 0; mm < N; ++mm) u[mm] = 0.0f;
+      for (int m2 = 0; m2 < N / 2; ++m2) up[m2] = p2(0.0f, 0.0f);
 #pragma unroll
-    for (int k = 0; k < N; ++k)
+      for (int k = 0; k < N; ++k) {
+        const P2 zz = p2(zk[k], zk[k]);
 #pragma unroll
-      for (int mm = 0; mm < N; ++mm) u[mm] = fmaf(taps.c[k * N + mm], zk[k], u[mm]);
+        for (int m2 = 0; m2 < N / 2; ++m2) {
+          const float2 t = reinterpret_cast<const float2*>(taps.c)[(k * N) / 2 + m2];
+          up[m2] = p2_fma(p2(t.x, t.y), zz, up[m2]);
+        }
+      }
+#pragma unroll
+      for (int m2 = 0; m2 < N / 2; ++m2) p2_unpack(up[m2], u[2 * m2], u[2 * m2 + 1]);
+    }
     float v[2 * N];
 #pragma unroll
     for (int r = 0; r < 2 * N; ++r) {
