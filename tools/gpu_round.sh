@@ -22,5 +22,10 @@ for K in k_pqmf_analysis k_gram_tc k_voice_control; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -o gpurun_out/prof_${K}_$TAG $CMD > gpurun_out/ncu_full_${K}_$TAG.log 2>&1
   echo "ncu $K exit $?"
 done
+# BASELINE config 3 kernels (not on the bench.py step): PQMF synthesis N=3 / N=16, analysis N=16
+NCU="ncu --set full --clock-control none --import-source on"
+timeout 300 $NCU -k regex:k_pqmf_synthesis -s 2 -c 1 -o gpurun_out/prof_k_pqmf_synthesis_n3_$TAG python tools/prof_pqmf.py > gpurun_out/ncu_syn3_$TAG.log 2>&1; echo "ncu synthesis N=3 exit $?"
+timeout 300 $NCU -k regex:k_pqmf_synthesis -s 5 -c 1 -o gpurun_out/prof_k_pqmf_synthesis_n16_$TAG python tools/prof_pqmf.py > gpurun_out/ncu_syn16_$TAG.log 2>&1; echo "ncu synthesis N=16 exit $?"
+timeout 300 $NCU -k regex:k_pqmf_analysis -s 1 -c 1 -o gpurun_out/prof_k_pqmf_analysis_n16_$TAG python tools/prof_pqmf_analysis.py > gpurun_out/ncu_ana16_$TAG.log 2>&1; echo "ncu analysis N=16 exit $?"
 ls -la gpurun_out | head -40
 timeout 600 python tools/bench_configs.py > gpurun_out/configs_$TAG.jsonl 2> gpurun_out/configs_$TAG.err; echo "configs exit $?"
