@@ -78,6 +78,39 @@ def test_new_entry_points_validate_arguments_without_a_gpu(built_lib):
         voice(0)  # parameters live on the CPU until .to(device): no CPU render path exists
 
 
+def test_round3_entry_points_validate_arguments_without_a_gpu(built_lib):
+    """ias_pqmf_analysis_pooled / ias_voice_render_stages / the prototype argument of ias_pqmf_synthesis: argument
+    checks run before any CUDA call; the Python mirrors refuse CPU tensors."""
+    import ias_b200
+
+    lib = ias_b200.lib()
+    rc = lib.ias_pqmf_analysis_pooled(None, None, None, None, None, None, None, None, 256, None, 0, 4, 1000, 3, 63, None)
+    assert rc == 1 and b"ias_pqmf_analysis_pooled" in lib.ias_last_error()
+    # workspace: two floats per (sound, band, CTA tile) of the smallest tile any kernel uses (256 steps)
+    assert lib.ias_pqmf_pool_workspace_bytes(1024, 176400, 3, 63) == 1024 * 3 * ((58800 + 255) // 256) * 2 * 4
+    assert lib.ias_pqmf_pool_workspace_bytes(0, 176400, 3, 63) == 0
+    rc = lib.ias_voice_render_stages(None, None, 0, None, None, 1, 100, 10, 44100.0, 441.0, 1e-6, 1, None, None, None, 0,
+                                     0, None)
+    assert rc == 1 and b"stages" in lib.ias_last_error()
+    rc = lib.ias_voice_render_stages(None, None, 0, None, None, 1, 1000, 10, 44100.0, 441.0, 1e-6, 1, None, None, None,
+                                     0, 1, None)  # control stage only: params01 is still required
+    assert rc == 1
+    rc = lib.ias_pqmf_synthesis(None, None, None, None, None, 0, 10, 16, 63, None)
+    assert rc == 1 and b"ias_pqmf_synthesis" in lib.ias_last_error()
+    gram = ias_b200.PQMF(N=3)
+    with pytest.raises(ias_b200.IasError):
+        gram.analysis_pooled(torch.zeros(2, 1, 200000), 256)
+    with pytest.raises(ValueError):
+        gram.analysis_pooled(torch.zeros(2, 200000), 256)
+    voice = ias_b200.Voice(synthconfig=ias_b200.SynthConfig(batch_size=32, reproducible=True, buffer_size_seconds=0.1))
+    with pytest.raises(ias_b200.IasError):
+        voice.prepare(0)
+    with pytest.raises(RuntimeError):
+        voice(0, prepared=True)  # nothing was prepared
+    with pytest.raises(ValueError):
+        voice.prepare(None)
+
+
 def test_voice_tables_match_oracle(built_lib):
     import ias_b200
 
