@@ -238,7 +238,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   constexpr int SPAN4 = (SPAN + 3) / 4;
   __shared__ __align__(16) float xs[Pad<S>::floats(SPAN4 * 4)];
   __shared__ int s_bound[POOL ? N : 1][2];                        // per band: start of bin ilo+1, end of bin ilo
-  __shared__ __align__(16) float s_pool[POOL ? 2 * N : 1][POOL ? PQ_THREADS : 4];  // per-thread sums, [band, slot] rows
+  __shared__ __align__(16) float s_pool[POOL ? N : 1][POOL ? PQ_THREADS : 4];  // per-thread sums of |v|, one row per band
+  __shared__ float s_mix[POOL ? N : 1][PQ_THREADS / 32][2];                    // bin-slot sums of boundary warps
 
   const int b = blockIdx.x / tiles_per_row;
   const int tile = blockIdx.x - b * tiles_per_row;
@@ -403,44 +404,73 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   }
 
   if constexpr (POOL) {
-    const int warp = threadIdx.x >> 5;
+    constexpr int NW = PQ_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool full = n_tile + TILE_N <= L;  // CTA-uniform: every step of the tile exists
     const int nv = L - n0;                   // else: valid steps of this thread = min(nv, Q)
+    // Per thread and band one value (the sum of its |v|) goes to shared memory; a warp whose 32*Q elements all lie in
+    // one bin (the usual case: bins are ~5 warps wide) is credited to that bin as a whole after the barrier.  Only a
+    // warp that straddles the bin boundary splits its sum itself (shuffle tree) into s_mix.
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const int s1 = s_bound[k][0], e0 = s_bound[k][1];
-      const int wfirst = k * L + n_tile + warp * 32 * Q, wlast = wfirst + 32 * Q - 1;
       float a[Q];
 #pragma unroll
       for (int q = 0; q < Q; ++q) a[q] = (full || q < nv) ? fabsf(acc[q][k]) : 0.0f;
-      float sum0, sum1;
-      if (wlast < s1 || wfirst >= e0) {  // the whole warp lies in one bin (warp-uniform branch)
-        float t = a[0];
+      float t = a[0];
 #pragma unroll
-        for (int q = 1; q < Q; ++q) t += a[q];
-        sum0 = wlast < s1 ? t : 0.0f;
-        sum1 = wlast < s1 ? 0.0f : t;
-      } else {
+      for (int q = 1; q < Q; ++q) t += a[q];
+      s_pool[k][threadIdx.x] = t;
+      const int s1 = s_bound[k][0], e0 = s_bound[k][1];
+      const int wfirst = k * L + n_tile + warp * 32 * Q, wlast = wfirst + 32 * Q - 1;
+      if (!(wlast < s1 || wfirst >= e0)) {  // warp-uniform: this warp straddles the boundary of band k
         const int f0 = k * L + n0;
-        sum0 = sum1 = 0.0f;
+        float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           sum0 += (f0 + q < e0) ? a[q] : 0.0f;
           sum1 += (f0 + q >= s1) ? a[q] : 0.0f;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sum0 += __shfl_xor_sync(0xffffffffu, sum0, o);
+          sum1 += __shfl_xor_sync(0xffffffffu, sum1, o);
+        }
+        if (lane == 0) {
+          s_mix[k][warp][0] = sum0;
+          s_mix[k][warp][1] = sum1;
+        }
       }
-      s_pool[2 * k][threadIdx.x] = sum0;
-      s_pool[2 * k + 1][threadIdx.x] = sum1;
     }
     __syncthreads();
-    // row r = (band, slot): 128 per-thread sums -> one value, fixed order (4 per lane, then a shuffle tree)
-    for (int r = warp; r < 2 * N; r += PQ_THREADS / 32) {
-      const int lane = threadIdx.x & 31;
+    // band r: lanes 8w..8w+7 hold the 32 per-thread sums of source warp w (4 each); three shuffle steps give the
+    // per-warp sums, which lane 0 credits to the two bin slots in warp order
+    for (int r = warp; r < N; r += NW) {
       const float4 v = *reinterpret_cast<const float4*>(&s_pool[r][4 * lane]);
       float t = (v.x + v.y) + (v.z + v.w);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      float wsum[NW];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) pool.partial[(((size_t)b * N + (r >> 1)) * tiles_per_row + tile) * 2 + (r & 1)] = t;
+      for (int w = 0; w < NW; ++w) wsum[w] = __shfl_sync(0xffffffffu, t, 8 * w);
+      if (lane == 0) {
+        const int s1 = s_bound[r][0], e0 = s_bound[r][1];
+        float slot0 = 0.0f, slot1 = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const int wfirst = r * L + n_tile + w * 32 * Q, wlast = wfirst + 32 * Q - 1;
+          if (wlast < s1) {
+            slot0 += wsum[w];
+          } else if (wfirst >= e0) {
+            slot1 += wsum[w];
+          } else {
+            slot0 += s_mix[r][w][0];
+            slot1 += s_mix[r][w][1];
+          }
+        }
+        float* dst = pool.partial + (((size_t)b * N + r) * tiles_per_row + tile) * 2;
+        *reinterpret_cast<float2*>(dst) = make_float2(slot0, slot1);
+      }
     }
   }
 }
