@@ -406,8 +406,15 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   if constexpr (POOL) {
     constexpr int NW = PQ_THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool full = n_tile + TILE_N <= L;  // CTA-uniform: every step of the tile exists
-    const int nv = L - n0;                   // else: valid steps of this thread = min(nv, Q)
+    if (n_tile + TILE_N > L) {  // last tile of a row (CTA-uniform, rare): steps past the end contribute nothing
+      const int nv = L - n0;
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (q >= nv) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc[q][k] = 0.0f;
+        }
+    }
     // Per thread and band one value (the sum of its |v|) goes to shared memory; a warp whose 32*Q elements all lie in
     // one bin (the usual case: bins are ~5 warps wide) is credited to that bin as a whole after the barrier.  Only a
     // warp that straddles the bin boundary splits its sum itself (shuffle tree) into s_mix.
@@ -415,7 +422,7 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
     for (int k = 0; k < N; ++k) {
       float a[Q];
 #pragma unroll
-      for (int q = 0; q < Q; ++q) a[q] = (full || q < nv) ? fabsf(acc[q][k]) : 0.0f;
+      for (int q = 0; q < Q; ++q) a[q] = fabsf(acc[q][k]);
       float t = a[0];
 #pragma unroll
       for (int q = 1; q < Q; ++q) t += a[q];
@@ -450,24 +457,25 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
       t += __shfl_xor_sync(0xffffffffu, t, 1);
       t += __shfl_xor_sync(0xffffffffu, t, 2);
       t += __shfl_xor_sync(0xffffffffu, t, 4);
-      float wsum[NW];
+      // every lane resolves the bin slots of its own source warp (lane >> 3) in parallel; lane 0 then adds the NW
+      // contributions in warp order
+      static_assert(NW == 4, "8 lanes per source warp");
+      const int sw = lane >> 3;
+      const int s1 = s_bound[r][0], e0 = s_bound[r][1];
+      const int wfirst = r * L + n_tile + sw * 32 * Q, wlast = wfirst + 32 * Q - 1;
+      const bool lo = wlast < s1, hi = wfirst >= e0;
+      float c0 = lo ? t : 0.0f, c1 = hi ? t : 0.0f;
+      if (!lo && !hi) {
+        c0 = s_mix[r][sw][0];
+        c1 = s_mix[r][sw][1];
+      }
+      float slot0 = __shfl_sync(0xffffffffu, c0, 0), slot1 = __shfl_sync(0xffffffffu, c1, 0);
 #pragma unroll
-      for (int w = 0; w < NW; ++w) wsum[w] = __shfl_sync(0xffffffffu, t, 8 * w);
+      for (int w = 1; w < NW; ++w) {
+        slot0 += __shfl_sync(0xffffffffu, c0, 8 * w);
+        slot1 += __shfl_sync(0xffffffffu, c1, 8 * w);
+      }
       if (lane == 0) {
-        const int s1 = s_bound[r][0], e0 = s_bound[r][1];
-        float slot0 = 0.0f, slot1 = 0.0f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          const int wfirst = r * L + n_tile + w * 32 * Q, wlast = wfirst + 32 * Q - 1;
-          if (wlast < s1) {
-            slot0 += wsum[w];
-          } else if (wfirst >= e0) {
-            slot1 += wsum[w];
-          } else {
-            slot0 += s_mix[r][w][0];
-            slot1 += s_mix[r][w][1];
-          }
-        }
         float* dst = pool.partial + (((size_t)b * N + r) * tiles_per_row + tile) * 2;
         *reinterpret_cast<float2*>(dst) = make_float2(slot0, slot1);
       }
