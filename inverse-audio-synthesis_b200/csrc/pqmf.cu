@@ -117,7 +117,17 @@ struct PoolArgs {
   float* partial;  // [B][N][tiles][2]
   int P;
   int S;  // N * L  (S * P < 2^31 is checked by the caller)
+  // floor(x / S) and floor(x / P) for x < 2^31 as __umulhi(x, m) >> sh with m = ceil(2^(32+sh) / d), 2^(sh+1) >= d
+  // (Granlund-Montgomery: exact for 31-bit x); the divisors are launch constants, so the host prepares (m, sh)
+  unsigned mS, shS, mP, shP;
 };
+__device__ __forceinline__ unsigned magic_div(unsigned x, unsigned m, unsigned sh) { return __umulhi(x, m) >> sh; }
+inline void magic_for(unsigned d, unsigned& m, unsigned& sh) {  // d >= 2
+  unsigned l = 1;
+  while ((1ull << l) < d) ++l;
+  m = (unsigned)(((1ull << (31 + l)) + d - 1) / d);
+  sh = l - 1;
+}
 
 // Shared-memory layout of a staged signal row.  Thread t reads a sliding window that starts at linear index t*S.
 //   S % 4 == 0: rows are stored in chunks of S floats at a padded pitch SP (a multiple of 4 with SP/4 odd), so the
@@ -255,9 +265,9 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   if constexpr (POOL) {
     if (threadIdx.x < N) {  // 32-bit arithmetic: S * P < 2^31 (checked by the launcher)
       const unsigned first = (unsigned)((int)threadIdx.x * L + n_tile);
-      const unsigned ilo = (first * (unsigned)pool.P) / (unsigned)pool.S;
+      const unsigned ilo = magic_div(first * (unsigned)pool.P, pool.mS, pool.shS);
       const unsigned num = (ilo + 1u) * (unsigned)pool.S;
-      const unsigned q = num / (unsigned)pool.P;
+      const unsigned q = magic_div(num, pool.mP, pool.shP);
       s_bound[threadIdx.x][0] = (int)q;
       s_bound[threadIdx.x][1] = (int)(q + (num - q * (unsigned)pool.P != 0u ? 1u : 0u));
     }
@@ -898,10 +908,10 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
   constexpr int TILE_N = PQ_THREADS * Q;
   const int tiles = (L + TILE_N - 1) / TILE_N;
   const unsigned grid = (unsigned)((size_t)B * tiles);
-  PoolArgs pool{nullptr, 0, 0};
+  PoolArgs pool{nullptr, 0, 0, 0, 0, 0, 0};
   if (pr) {
     const long long S = (long long)N * L;
-    IAS_REQUIRE(pr->P > 0 && S * pr->P < (1LL << 31) && TILE_N + 1 <= S / pr->P, IAS_ERR_UNSUPPORTED,
+    IAS_REQUIRE(pr->P > 1 && S * pr->P < (1LL << 31) && TILE_N + 1 <= S / pr->P, IAS_ERR_UNSUPPORTED,
                 "ias_pqmf_analysis_pooled: P=%d needs bins wider than the %d-step CTA tile (N*L=%lld)", pr->P, TILE_N, S);
     const size_t need = (size_t)B * N * tiles * 2 * sizeof(float);
     IAS_REQUIRE(pr->workspace && pr->workspace_bytes >= need, IAS_ERR_INVALID,
@@ -909,6 +919,8 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
     pool.partial = static_cast<float*>(pr->workspace);
     pool.P = pr->P;
     pool.S = (int)S;
+    magic_for((unsigned)S, pool.mS, pool.shS);
+    magic_for((unsigned)pr->P, pool.mP, pool.shP);
   }
   BandNorm<N> norm;
   norm.on = (mean_host && std_host) ? 1 : 0;
