@@ -507,10 +507,13 @@ def run_ours(args):
         "loss4_last_step": loss_vals,
     }
     if not args.no_cpu_baseline and world == 1:
-        v, ms, stage = cpu_step_rate(args.cpu_sample, args.bands, args.seconds, steps=3, warmup=1)
+        # bounded sample: 30 steps x 128 sounds, about 10 s of host work on the box's 16 cores
+        cpu_steps = 30
+        v, ms, stage = cpu_step_rate(args.cpu_sample, args.bands, args.seconds, steps=cpu_steps, warmup=2)
         line["cpu_baseline"] = {
             "value": v, "unit": "sounds/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{args.cpu_sample} sounds x {args.seconds:g} s per step x 3 steps (BASELINE configs[0]) through oracle/",
+            "sample": f"{args.cpu_sample} sounds x {args.seconds:g} s per step x {cpu_steps} steps (BASELINE configs[0]) through "
+                      "oracle/ (torch fp32 Voice restatement -> torch conv1d PQMF -> bridge -> torch VICReg ops)",
             "ms_per_step": ms, "stage_ms": stage}
     print(json.dumps(line))
     if world > 1:
