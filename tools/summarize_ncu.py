@@ -81,8 +81,9 @@ def full_summaries(tag):
                               "capture": os.path.basename(rep)}
         except Exception:
             pass
-    with open(os.path.join(PROF, f"{tag}_ncu_full_summary.md"), "w") as f:
-        f.write("\n".join(lines) + "\n")
+    if len(lines) > 1:  # a session without full captures (tools/gpu_final.sh) leaves no empty summary behind
+        with open(os.path.join(PROF, f"{tag}_ncu_full_summary.md"), "w") as f:
+            f.write("\n".join(lines) + "\n")
     if traffic:
         path = os.path.join(PROF, "traffic.json")
         old = {}
@@ -131,7 +132,8 @@ def launch_list(tag):
 
 def copy_logs(tag):
     for pat in (f"bench_{tag}.json", f"bench_ref_{tag}.json", f"smoke_{tag}.log", f"test_*_{tag}.log",
-                f"bench_g*_{tag}.json", f"multi_check_{tag}.log", f"topo_{tag}.txt", f"configs_{tag}.json"):
+                f"bench_g*_{tag}.json", f"multi_check_{tag}.log", f"topo_{tag}.txt", f"configs_{tag}.json",
+                f"configs_{tag}.jsonl"):
         for p in glob.glob(os.path.join(OUT, pat)):
             if os.path.getsize(p) < 200_000:
                 shutil.copy(p, os.path.join(PROF, os.path.basename(p)))
