@@ -45,10 +45,18 @@ def parse():
     ap.add_argument("--pipeline", action="store_true",
                     help="overlap the next batch's control stage (Voice.prepare, side stream) with this batch's PQMF / "
                          "loss; measured +2.3 %% (1.250 -> 1.222 ms/step), off by default so a step is self-contained")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
-                    help="N>1: fused = loss kernels read peers' embeddings over NVLink (symmetric memory); "
-                         "nccl = FullGatherLayer all-gather through torch.distributed")
-    ap.add_argument("--cpu-sample", type=int, default=128, help="sounds per CPU-baseline step (config 1: 128)")
+    ap.add_argument("--gather", default="stats", choices=["stats", "peer", "nccl"],
+                    help="N>1 embedding exchange: stats = every rank reduces its own rows and pushes a 0.4 MB summary "
+                         "(mean, second moments, Gram) to its peers over NVLink from inside the loss kernels; peer = the "
+                         "statistics kernel reads every peer's embeddings over NVLink (symmetric memory); nccl = "
+                         "FullGatherLayer all-gather through torch.distributed (NCCL)")
+    ap.add_argument("--cpu-sample", type=int, default=128,
+                    help="sounds per CPU chunk (BASELINE configs[0]: 128); the reference arm renders --batch-per-gpu "
+                         "sounds per step in chunks of this size, the in-run cpu_baseline leg one chunk per step")
+    ap.add_argument("--no-nonreproducible", action="store_true", help="skip the reproducible=False e2e variant")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (outside the timed region)")
+    ap.add_argument("--parity-sounds", type=int, default=0,
+                    help="sounds of the parity block's CPU oracle render (default: 128 at 4 s, 16 for long clips)")
     return ap.parse_args()
 
 
@@ -56,18 +64,40 @@ def parse():
 # clocks during the timed region
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons while the timed region runs.  NVML from a thread every 5 ms (the driver's
+    --steps 20 timed region is ~25 ms: `nvidia-smi -lms 100` sees it once); nvidia-smi only if NVML is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReasons bits
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []  # (arrival wall-clock, csv line)
+        self.rows = []      # nvidia-smi: (arrival wall-clock, csv line)
+        self.samples = []   # NVML: (wall-clock, sm_mhz, reasons bitmask)
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
         self.t_begin = None
         self.t_end = None
+        self.max_mhz = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+            self.thread = threading.Thread(target=self._pump_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
@@ -77,13 +107,26 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _pump_nvml(self):
+        pynvml, h = self.nvml
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.samples.append((time.time(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                     int(get_reasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def wait_first_sample(self, timeout=5.0):
         t0 = time.time()
-        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+        while (self.proc is not None or self.nvml is not None) and not (self.rows or self.samples) and \
+                time.time() - t0 < timeout:
             time.sleep(0.02)
 
     def mark_begin(self):
@@ -93,6 +136,18 @@ class ClockSampler:
         self.t_end = time.time()
 
     def stop(self):
+        self.stop_flag = True
+        lo = (self.t_begin or 0.0)
+        if self.nvml is not None:
+            hi = (self.t_end or 1e30) + 0.002
+            inside = [(m, r) for t, m, r in self.samples if lo <= t <= hi] or [(m, r) for _, m, r in self.samples[-3:]]
+            sm = sorted(m for m, _ in inside)
+            mask = 0
+            for _, r in inside:
+                mask |= r
+            reasons = sorted(k for k, b in self.BITS.items() if mask & b)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 5 ms period, samples inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -101,7 +156,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        lo = (self.t_begin or 0.0)
         hi = (self.t_end or 1e30) + 0.15  # a sample describes the ~100 ms before it arrives
         rows = [r for t, r in self.rows if lo <= t <= hi] or [r for _, r in self.rows[-3:]]
         for r in rows:
@@ -118,43 +172,78 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # CPU reference arm / baseline (oracle on the host cores)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_step_rate(sample: int, bands: int, seconds: float, steps: int, warmup: int):
+def cpu_step_rate(chunk: int, bands: int, seconds: float, steps: int, warmup: int, sounds_per_step: int = 0):
+    """Oracle front end on the host cores.  One step = `sounds_per_step` sounds (default: one chunk) rendered and
+    filtered in chunks of `chunk` sounds (bounds the host memory: the torch restatement of the synth keeps ~25
+    [chunk, T] fp32 intermediates alive), then the bridge projections and ONE VICReg loss over the step's embeddings.
+    -> (sounds/s, ms per step, per-stage ms per step)."""
     torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import vicreg as OV
+
+    sounds_per_step = sounds_per_step or chunk
+    nchunks = max(1, (sounds_per_step + chunk - 1) // chunk)
     times = []
     stage = {}
     for i in range(warmup + steps):
         t = {}
         t0 = time.perf_counter()
-        harness.oracle_front_end(i, sample, N=bands, seconds=seconds, timings=t, torch_ops=True)
+        xs, ys = [], []
+        for c in range(nchunks):
+            tc = {}
+            n = min(chunk, sounds_per_step - c * chunk)
+            # chunk c of step i = batch number i * nchunks + c of a batch-size-`chunk` Voice: the same sound ids as one
+            # batch of `sounds_per_step` sounds (ids are batch_idx * B + row, SURVEY A.2) when chunk divides it
+            r = harness.oracle_front_end(i * nchunks + c, n, N=bands, seconds=seconds, timings=tc, torch_ops=True,
+                                         cfg_batch=sounds_per_step)
+            xs.append(r["x"])
+            ys.append(r["y"])
+            for k, v in tc.items():
+                t[k] = t.get(k, 0.0) + v
+        if nchunks > 1:  # the loss of the step sees all of its sounds (the per-chunk value above is discarded)
+            tl = time.perf_counter()
+            OV.loss_torch(torch.cat(xs), torch.cat(ys), sounds_per_step, harness.EMBED_DIM)
+            t["vicreg"] = t.get("vicreg", 0.0) + time.perf_counter() - tl
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
             for k, v in t.items():
                 stage[k] = stage.get(k, 0.0) + v
     total = sum(times)
-    return sample * len(times) / total, total / len(times) * 1e3, {k: v / len(times) * 1e3 for k, v in stage.items()}
+    return (sounds_per_step * len(times) / total, total / len(times) * 1e3,
+            {k: v / len(times) * 1e3 for k, v in stage.items()})
+
+
+def workload_name(bands: int, seconds: float, per_gpu: int, world: int, exchange: str) -> str:
+    return ("BASELINE configs[%d] shard: front end synth->PQMF(N=%d)->VICReg(D=256), %d sounds x %g s @ 44.1 kHz per GPU, "
+            "global batch %d, embedding exchange %s" % (4 if seconds > 4.0 else 3, bands, per_gpu, seconds,
+                                                        per_gpu * world, exchange))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, stage = cpu_step_rate(args.cpu_sample, args.bands, args.seconds, args.steps, args.warmup)
+    per_step = args.batch_per_gpu
+    value, ms, stage = cpu_step_rate(args.cpu_sample, args.bands, args.seconds, args.steps, args.warmup,
+                                     sounds_per_step=per_step)
     cores = torch.get_num_threads()
-    sample = (f"{args.cpu_sample} sounds x {args.seconds:g} s per step (BASELINE configs[0]), oracle/ CPU path: torch fp32 "
-              f"Voice restatement -> torch conv1d PQMF -> bridge -> torch VICReg ops, {cores} threads")
+    sample = (f"{per_step} sounds x {args.seconds:g} s per step in chunks of {args.cpu_sample} (BASELINE configs[0] is one "
+              f"chunk), oracle/ CPU path: torch fp32 Voice restatement -> torch conv1d PQMF -> bridge -> torch VICReg ops "
+              f"on the step's {per_step} embeddings, {cores} threads")
     line = {
         "impl": "reference", "metric": "4s@44.1kHz sounds/sec (synth->PQMF->VICReg)", "value": value,
         "unit": "sounds/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "front end synth->PQMF(N=%d)->VICReg(D=256), %g s voices, CPU sample of %d sounds/step"
-                   % (args.bands, args.seconds, args.cpu_sample)},
+        "config": {"workload": workload_name(args.bands, args.seconds, per_step, 1, "n/a (CPU reference arm: one "
+                                             "process, one shard; rates are per sound)"),
+                   "per_gpu_batch": per_step, "seconds": args.seconds, "bands": args.bands,
+                   "cpu_chunk": args.cpu_sample},
         "cpu_baseline": {"value": value, "unit": "sounds/s", "cores": cores, "kind": "port", "sample": sample,
                          "stage_ms": stage},
         "e2e": {"value": value, "unit": "sounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -166,6 +255,107 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
+def source_hash() -> str:
+    """sha256 over the kernel sources of the build being benchmarked (ties committed ncu captures to a build)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = os.path.join(harness.PKG, "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".cpp")):
+            h.update(name.encode())
+            h.update(open(os.path.join(csrc, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def parity_block(args, rank, world, dev, voice, gram, vic, wa, wp):
+    """Results against the CPU oracle, OUTSIDE every timed region (SURVEY 8c tolerances).  Every N:
+    the four loss terms each rank computed through the route that was timed (statistics exchange / peer gather / NCCL)
+    against the float64 oracle on the rank-ordered concatenation of all ranks' embeddings (gathered here with a plain
+    NCCL all-gather) -- the N-rank == 1-rank semantics of FullGatherLayer (vicreg.py:38-39,79-95).  Rank 0 additionally
+    renders a small batch on the CPU oracle and checks audio, PQMF bands and loss terms of the GPU path against it.
+    -> (dict for the JSON line, list of violated bounds)."""
+    import numpy as np
+    import torch.distributed as dist
+
+    import ias_b200
+    from oracle import vicreg as OV
+
+    B = voice.batch_size
+    failures = []
+    out = {"where": "after the timed regions, not included in any reported time"}
+    # ---- exchange route: N ranks == oracle on the concatenation ----
+    batch_no = 900_001
+    audio, params, _ = voice(batch_no * world + rank)
+    _, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
+    with torch.no_grad():
+        l4 = torch.stack(vic.loss(x, y)).double()
+    xy = torch.cat([x, y], dim=1).contiguous()
+    if world > 1:
+        xy_all = torch.empty((world,) + tuple(xy.shape), dtype=xy.dtype, device=dev)
+        dist.all_gather_into_tensor(xy_all.view(-1), xy.view(-1))
+        l4_all = torch.empty((world, 4), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(l4_all.view(-1), l4.contiguous())
+    else:
+        xy_all, l4_all = xy[None], l4[None]
+    if rank == 0:
+        xa = xy_all[:, :, :D].reshape(world * B, D).double().cpu().numpy()
+        ya = xy_all[:, :, D:].reshape(world * B, D).double().cpu().numpy()
+        got = l4_all.cpu().numpy()
+        rel = np.zeros(4)
+        for r in range(world):
+            want = np.array(OV.loss(xa, ya, world * B, D, local_rows=slice(r * B, (r + 1) * B)))
+            rel = np.maximum(rel, np.abs(got[r] - want) / np.abs(want))
+        same = bool(np.all(got[:, 2:] == got[0, 2:]))
+        out["exchange"] = {
+            "route": (args.gather if world > 1 else "single process"), "ranks": world, "global_batch": world * B,
+            "loss4_rel": [float(v) for v in rel], "std_cov_identical_across_ranks": same,
+            "oracle": "oracle/vicreg.py float64 on the concatenation of every rank's embeddings (plain NCCL all-gather)",
+            "bound": 1e-4}
+        if not (np.all(rel <= 1e-4) and same):
+            failures.append("exchange loss4_rel %s identical=%s" % (rel, same))
+        # ---- rank 0: a small batch against the CPU oracle ----
+        P = args.parity_sounds or (128 if args.seconds <= 4.0 else 16)
+        Bv = (P + 31) // 32 * 32  # reproducible mode renders multiples of 32; the first P rows are compared
+        ref = harness.oracle_front_end(0, P, N=args.bands, seconds=args.seconds, cfg_batch=P)
+        cfgP = ias_b200.SynthConfig(batch_size=Bv, reproducible=True, sample_rate=44100,
+                                    buffer_size_seconds=args.seconds)
+        vP = ias_b200.Voice(synthconfig=cfgP).to(dev)
+        vcfg = types.SimpleNamespace(dim=D, embeddim=D, vicreg=types.SimpleNamespace(
+            mlp="8-8-%d", batch_size=P, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
+        vicP = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity(), gather=False)
+        a, prm, _ = vP(0)
+        a, prm = a[:P].contiguous(), prm[:P].contiguous()
+        err = (a.cpu() - ref["audio"]).abs().max(dim=1)[0]
+        bands_ref_in = gram(ref["audio"].unsqueeze(1).to(dev)).cpu()
+        pq = float((bands_ref_in - ref["bands"]).abs().max() / ref["bands"].abs().max())
+        want = np.array(ref["loss4"])
+        with torch.no_grad():
+            g_or = np.array([float(v) for v in vicP.loss(ref["x"].to(dev), ref["y"].to(dev))])
+            _, xg, yg = harness.analysis_bridge(gram, a, prm, wa, wp)
+            g_e2e = np.array([float(v) for v in vicP.loss(xg, yg)])
+        rel_or = np.abs(g_or - want) / np.abs(want)
+        rel_e2e = np.abs(g_e2e - want) / np.abs(want)
+        out["oracle_batch"] = {
+            "sounds": P, "seconds": args.seconds, "params_bit_equal": bool(torch.equal(prm.cpu(), ref["params"])),
+            "voices_le_1e-4": int((err <= 1e-4).sum()), "audio_median": float(err.median()),
+            "audio_max": float(err.max()), "pqmf_rel": pq, "loss4_rel_on_oracle_embeddings": [float(v) for v in rel_or],
+            "loss4_rel_end_to_end": [float(v) for v in rel_e2e],
+            "bounds": {"audio": 1e-4, "pqmf_rel": 1e-5, "loss4_rel": 1e-4},
+            "note": "oracle = oracle/ on this box's CPU (torch fp32 Voice restatement, parity unpinned w.r.t. torchsynth; "
+                    "numpy float64 PQMF and loss).  Voices above 1e-4 trace to 1-ulp LFO cosine differences amplified by "
+                    "the pitch path (DESIGN.md 4); the end-to-end loss terms inherit them."}
+        if not out["oracle_batch"]["params_bit_equal"]:
+            failures.append("seeded parameters differ from torch's CPU generator")
+        if float(err.median()) > 1e-5:
+            failures.append("audio median error %g" % float(err.median()))
+        if pq > 1e-5:
+            failures.append("pqmf_rel %g" % pq)
+        if not np.all(rel_or <= 1e-4):
+            failures.append("loss4 on oracle embeddings %s" % rel_or)
+    return out, failures
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -194,8 +384,19 @@ def run_ours(args):
         mlp="8-8-%d", batch_size=B * world, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
     vic = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity())
     wa, wp = harness.bridge_weights(dev)
-    if world > 1 and args.gather == "fused":
-        ias_b200.use_fused_gather(ias_b200.EmbeddingExchange(B, D, dev))
+    exchange_desc = "n/a at N=1"
+    if world > 1:
+        if args.gather == "stats":
+            ias_b200.use_fused_gather(ias_b200.StatsExchange(D, dev))
+            exchange_desc = ("statistics exchange: per-rank mean / second moments / tcgen05 Gram pushed to every peer over "
+                             "NVLink by the loss kernels (0.39 MB per rank and step), pooled on arrival; no NCCL on the "
+                             "data path (NCCL carries only process-group setup and the timing all-reduce)")
+        elif args.gather == "peer":
+            ias_b200.use_fused_gather(ias_b200.EmbeddingExchange(B, D, dev))
+            exchange_desc = ("fused into the loss kernels: the column-statistics kernel reads every peer's embeddings over "
+                             "NVLink peer memory; no NCCL on the data path")
+        else:
+            exchange_desc = "NCCL all-gather of the embeddings (FullGatherLayer through torch.distributed)"
 
     def step(i: int):
         audio, params, _ = voice(i * world + rank)       # sound ids [ (i*W + r) * B, ... ): SURVEY 8(d) config 4
@@ -427,7 +628,50 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_params_ms = float(t.item())
 
+    # ---- variant: the reference's own noise mode, reproducible=False: a [B,T] table read from HBM every step ----
+    e2e_nr_ms, nr_mode = None, None
+    if not args.no_nonreproducible:
+        cfg_nr = ias_b200.SynthConfig(batch_size=B, reproducible=False, sample_rate=44100,
+                                      buffer_size_seconds=args.seconds)
+        voice_nr = ias_b200.Voice(synthconfig=cfg_nr).to(dev)
+
+        def step_e2e_nr():
+            idx_dev.copy_(host_in, non_blocking=True)
+            audio, params, _ = voice_nr(idx_dev)
+            bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
+            with torch.no_grad():
+                out = torch.stack(vic.loss(x, y))
+            host_out.copy_(out, non_blocking=True)
+            return out
+
+        graph_nr, _, nr_mode = capture(step_e2e_nr)
+
+        def run_nr(j):
+            host_in[0] = batch_numbers[j]
+            if graph_nr is not None:
+                graph_nr.replay()
+            else:
+                step_e2e_nr()
+            stream.synchronize()
+
+        for j in range(min(3, args.steps)):
+            run_nr(j)
+        sync()
+        e0.record()
+        for j in range(args.steps):
+            run_nr(j)
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_nr_ms = float(t.item())
+        del voice_nr, graph_nr
+
     clocks = sampler.stop() if rank == 0 else None
+    parity, parity_failures = (None, [])
+    if not args.no_parity:
+        parity, parity_failures = parity_block(args, rank, world, dev, voice, gram, vic, wa, wp)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -449,11 +693,38 @@ def run_ours(args):
     # 32-row L2-resident one in reproducible mode) x B sounds.
     voice_bytes = 4.0 * T * B
     achieved = voice_bytes / (va["ms_per_launch"] * 1e-3) / 1e9
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel
+    # dram__bytes_read.sum + dram__bytes_write.sum and the issue-side counters of one `ncu --set full` capture of this
+    # kernel (profiles/capture_k_voice_audio.json, written by tools/summarize_ncu.py).  Used only if the capture was
+    # taken from the very sources that are being benchmarked and on this workload shape; null otherwise.
+    traffic, issue, capture_note = None, None, "no capture of this build"
+    src = source_hash()
     try:
-        if B == 1024 and T == T_4S:
-            traffic = json.load(open(os.path.join(harness.ROOT, "profiles", "traffic.json")))["k_voice_audio"][
-                "per_launch_bytes"]
+        cap = json.load(open(os.path.join(harness.ROOT, "profiles", "capture_k_voice_audio.json")))
+        if cap.get("src_sha256") != src:
+            capture_note = "profiles/capture_k_voice_audio.json is of sources %s, this build is %s" % (
+                cap.get("src_sha256"), src)
+        elif not (B == cap.get("B") and T == cap.get("T")):
+            capture_note = "capture is of B=%s T=%s" % (cap.get("B"), cap.get("T"))
+        else:
+            traffic = cap.get("dram_bytes_per_launch")
+            capture_note = "ncu --set full capture %s of this build" % cap.get("run")
+            ipw = cap.get("inst_executed_per_launch")
+            if ipw:
+                # issue roofline (SURVEY 8d "report min(HBM, issue)"): warp instructions per sample from the capture,
+                # the dispatch-cycle cost of that mix (packed fp32 and half-rate ALU instructions hold a
+                # scheduler's dispatch port for two cycles), against what 4 schedulers x SMs x clock offer in the
+                # measured launch time
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                clk = (clocks or {}).get("sm_mhz") or cap.get("sm_mhz") or 1965.0
+                samples = float(B) * T
+                cyc = cap.get("dispatch_cycles_per_warp_instruction", 1.0) * ipw
+                avail = sms * 4 * clk * 1e6 * (va["ms_per_launch"] * 1e-3)
+                issue = {"instr_per_sample": ipw * 32.0 / samples, "warp_instructions_per_launch": ipw,
+                         "dispatch_cycles_model": cyc * 32.0 / samples, "achieved_frac": cyc / avail,
+                         "issue_slots_busy_pct_ncu": cap.get("issue_active_pct"),
+                         "pipes_pct_ncu": cap.get("pipes_pct"), "sm_mhz_used": clk,
+                         "note": "achieved_frac = modelled dispatch cycles / (SMs x 4 schedulers x clock x measured "
+                                 "launch time); instr_per_sample counts warp instructions x 32 lanes / samples"}
     except Exception:
         pass
     line = {
@@ -470,18 +741,22 @@ def run_ours(args):
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": ("BASELINE configs[3] shard: front end synth->PQMF(N=%d)->VICReg(D=256), %d sounds x %g s @ 44.1 kHz "
-                         "per GPU, global batch %d, embedding all-gather %s" % (
-                             args.bands, B, args.seconds, B * world, ("fused into the loss kernels over NVLink peer memory" if args.gather == "fused" else "over NCCL")
-                             if world > 1 else "n/a at N=1")),
+            "workload": workload_name(args.bands, args.seconds, B, world, exchange_desc),
             "per_gpu_batch": B, "global_batch": B * world, "seconds": args.seconds, "bands": args.bands,
-            "noise": "reproducible (32-row table)",
-            "l2": "inputs larger than L2: 722 MB audio + 722 MB bands per step vs 126 MB L2",
-            "bridge": "abs-mean pool to 256 bins (epilogue of k_pqmf_analysis + k_pool_finalize) + 2 torch matmuls (harness, not a reference component), inside the step",
+            "exchange": args.gather if world > 1 else None,
+            "noise": "reproducible (32-row table, L2 resident); the reference's reproducible=False ([B,T] table read "
+                     "from HBM) is timed beside it as e2e_nonreproducible",
+            "l2": "inputs larger than L2: %.0f MB audio + %.0f MB bands per step vs 126 MB L2" % (
+                4e-6 * B * T, 4e-6 * B * T),
+            "bridge": "abs-mean pool to 256 bins + 2 torch matmuls (harness, not a reference component), inside the "
+                      "step; device path taken: %s" % harness.LAST_BRIDGE_PATH,
+            "rates": "sounds/s: a rate per sound, comparable across batch sizes (the CPU reference arm renders the same "
+                     "per-GPU batch in chunks of %d sounds)" % args.cpu_sample,
         },
         "roofline": {
             "bound": "hbm", "kernel": "k_voice_audio", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+            "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": capture_note, "issue": issue,
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": voice_bytes,
             "ms_per_launch": va["ms_per_launch"],
             "note": "k_voice_audio is instruction-issue bound, not HBM bound (DESIGN.md); step-level fraction below",
@@ -498,6 +773,14 @@ def run_ours(args):
         "e2e_host_params": {"value": sounds / (e2e_params_ms * 1e-3), "unit": "sounds/s",
                             "h2d_bytes_per_step": 78 * B * 4, "d2h_bytes_per_step": 16,
                             "note": "same, but the [78,B] parameter block comes from pinned host memory every step"},
+        "e2e_nonreproducible": (None if e2e_nr_ms is None else {
+            "value": sounds / (e2e_nr_ms * 1e-3), "unit": "sounds/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 16,
+            "mode": nr_mode, "note": "same step with SynthConfig(reproducible=False), the reference's setting "
+                                     "(conf/config.yaml:38): noise is a [B,T] table (%.0f MB) streamed from HBM" % (
+                                         4e-6 * B * T)}),
+        "parity": parity,
+        "parity_ok": not parity_failures,
+        "src_sha256": src,
         "gpu_launches": launches,
         "gpu_launches_note": "%d kernel launches of libias_b200.so per step (counted by the library in the eager "
                              "profiling pass) x %d timed steps; the timed region issues them as %s" % (
@@ -508,16 +791,21 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         # bounded sample: 30 steps x 128 sounds, about 10 s of host work on the box's 16 cores
+        # bounded sample: 30 steps x 128 four-second sounds (16 thirty-second ones), about 10 s of host work
         cpu_steps = 30
-        v, ms, stage = cpu_step_rate(args.cpu_sample, args.bands, args.seconds, steps=cpu_steps, warmup=2)
+        chunk = args.cpu_sample if args.seconds <= 4.0 else max(8, int(args.cpu_sample * 4.0 / args.seconds) // 8 * 8)
+        v, ms, stage = cpu_step_rate(chunk, args.bands, args.seconds, steps=cpu_steps, warmup=2)
         line["cpu_baseline"] = {
             "value": v, "unit": "sounds/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{args.cpu_sample} sounds x {args.seconds:g} s per step x {cpu_steps} steps (BASELINE configs[0]) through "
+            "sample": f"{chunk} sounds x {args.seconds:g} s per step x {cpu_steps} steps (BASELINE configs[0]) through "
                       "oracle/ (torch fp32 Voice restatement -> torch conv1d PQMF -> bridge -> torch VICReg ops)",
             "ms_per_step": ms, "stage_ms": stage}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity_failures:
+        print("bench.py: PARITY FAILED: " + "; ".join(parity_failures), file=sys.stderr)
+        sys.exit(3)
 
 
 def main():

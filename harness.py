@@ -25,6 +25,7 @@ for _p in (ROOT, PKG):
 
 EMBED_DIM = 256
 NPARAMS = 78
+LAST_BRIDGE_PATH = None  # which device path analysis_bridge took last (recorded in the bench line)
 
 
 def bridge_weights(device="cpu") -> Tuple[torch.Tensor, torch.Tensor]:
@@ -53,15 +54,22 @@ def bridge(bands: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torc
 def analysis_bridge(gram, audio: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torch.Tensor):
     """Device path of ``bridge(gram(audio), params)`` with the pooling fused into the PQMF analysis kernel
     (``PQMF.analysis_pooled``): the bands make one trip to HBM.  -> (bands, x, y)."""
-    from ias_b200 import IasError
+    from ias_b200 import IasError, _lib
 
+    global LAST_BRIDGE_PATH
     x3 = audio.unsqueeze(1) if audio.dim() == 2 else audio
     try:
         bands, feat = gram.analysis_pooled(x3, EMBED_DIM)
-    except IasError:  # bins narrower than a CTA tile (short clips): unfused device kernels, same result
+    except IasError as exc:
+        # only "this shape has no fused kernel" (bins narrower than a CTA tile: short clips) may take the unfused
+        # device kernels; a launch failure, a workspace error or a missing library must surface
+        if exc.code != _lib.IAS_ERR_UNSUPPORTED:
+            raise
         bands = gram(x3)
         x, y = bridge(bands, params, wa, wp)
+        LAST_BRIDGE_PATH = "unfused: ias_pqmf_analysis + ias_abs_avg_pool"
         return bands, x, y
+    LAST_BRIDGE_PATH = "fused: ias_pqmf_analysis_pooled"
     return bands, feat @ wa, params @ wp
 
 

@@ -121,6 +121,10 @@ IAS_API int ias_pqmf_out_len(int T, int N, int K);
  * H[k][j] == proto[j] * mod[k][j % 2N]: when the caller knows H is the filter PQMF.__init__ designs (pqmf.py:18-30)
  * it passes them and the kernel runs the polyphase form (63 + 2N^2 instead of 63N multiply-adds per time step);
  * with NULL the direct form is used, valid for any H (e.g. taps loaded from a checkpoint).
+ * The fast kernels rebuild part of the modulation from PQMF.__init__'s own formula (N >= 8 never read mod_host), so a
+ * non-NULL factorisation is honoured only if it reproduces the H_host that is passed with that design (centre
+ * (taps-1)/2, phase (-1)^k pi/4; checked on the host, cached); any other cosine-modulated bank -- e.g. the textbook
+ * taps/2 centring of the reference's TODO at pqmf.py:26 -- runs the direct form.
  * row_scale[B] (may be NULL) multiplies row b of x, so normalize_if_clipping can be folded in (scale = 1/peak). */
 IAS_API int ias_pqmf_analysis(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
                       const float* mod_host, const float* row_scale, float* out, int B, int T, int N, int K,
@@ -152,7 +156,8 @@ IAS_API int ias_pqmf_analysis_pooled(const float* x, const float* H_dev, const f
 /* PQMF.synthesis (pqmf.py:52-55): zero-stuff by N with gain N, then the N->1 FIR G = [N][K] (buffer G[0]).
  * y[b][t], t < L*N.  proto_host[K] (host, optional) is the same signed prototype as in ias_pqmf_analysis: the caller
  * passes it when G is the filter PQMF.__init__ designs (pqmf.py:18-30), and N = 8 / 16 then run the cosine-modulated
- * form (size-N DCT-IV per time step + 63 multiply-adds, instead of 63 N); NULL = direct form, valid for any G. */
+ * form (size-N DCT-IV per time step + 63 multiply-adds, instead of 63 N); NULL = direct form, valid for any G.
+ * As for the analysis, proto_host is honoured only when G_host is the PQMF.__init__ design it factorises. */
 IAS_API int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, const float* proto_host, float* y,
                        int B, int L, int N, int K, ias_stream_t stream);
 
@@ -194,6 +199,31 @@ IAS_API int ias_vicreg_loss_gather_backward(int world, int rank, int B_local, in
                                     float sim_coeff, float std_coeff, float cov_coeff, const float* gout4,
                                     float* gx_local, float* gy_local, void* workspace, size_t workspace_bytes,
                                     ias_stream_t stream);
+
+/* Statistics exchange (the default multi-GPU route): the loss over the global batch without gathering the
+ * embeddings.  Each rank reduces its own [B_local][D] rows with the single-GPU kernels (local mean, locally-centred
+ * second moments and tcgen05 Gram), pushes that 4*Dp + 2*ntiles*128*128-float summary (0.39 MB at D = 256) into every
+ * rank's inbox with plain stores over NVLink, raises a flag there, and combines the `world` summaries it received with
+ * the exact pooled formulas  mu = sum_q B_q mu_q / B,  G = sum_q [G_q + B_q (mu_q - mu)(mu_q - mu)^T]  -- the same
+ * numbers (to fp32 rounding) as vicreg.py:40-51 on the rank-ordered concatenation that FullGatherLayer (vicreg.py:38-39,
+ * 79-95) would produce, with 1/W of the arithmetic per rank and no collective or barrier launch.
+ * buffers_host[q] (host array of `world` DEVICE pointers, rank order) is rank q's exchange buffer of
+ * ias_vicreg_stats_buffer_bytes(world, D) bytes in peer-accessible memory (e.g. torch symmetric memory), mapped into
+ * this process; the caller zero-fills its own buffer once, sets the int at byte offset 128 (the step counter) to 1 and
+ * synchronises all ranks before the first call.  Every rank must make the same sequence of calls (equal B_local).
+ * A rank whose peers never arrive traps after 30 s instead of hanging.  x, y: this rank's rows; invariance term on
+ * them (vicreg.py:36).  workspace: ias_vicreg_workspace_bytes(B_local, D), kept for the backward. */
+IAS_API size_t ias_vicreg_stats_buffer_bytes(int world, int D);
+IAS_API int ias_vicreg_loss_stats(const float* x, const float* y, float* const* buffers_host, int world, int rank,
+                          int B_local, int cfg_batch_size, int D, int embeddim, float sim_coeff, float std_coeff,
+                          float cov_coeff, float* out4, void* workspace, size_t workspace_bytes, ias_stream_t stream);
+/* Gradient w.r.t. this rank's rows summed over all ranks' losses (FullGatherLayer.backward, vicreg.py:92-95): the
+ * std/cov terms are identical on every rank, so it is `world` times the own-row slice -- no communication.  Same
+ * x, y and workspace as the preceding ias_vicreg_loss_stats. */
+IAS_API int ias_vicreg_loss_stats_backward(const float* x, const float* y, int world, int B_local, int cfg_batch_size,
+                                   int D, int embeddim, float sim_coeff, float std_coeff, float cov_coeff,
+                                   const float* gout4, float* gx_local, float* gy_local, void* workspace,
+                                   size_t workspace_bytes, ias_stream_t stream);
 
 /* Test hook: plain CUDA-core Gram of the centred matrix, gram[D][D] = xc^T xc, to cross-check the tcgen05 path. */
 IAS_API int ias_vicreg_gram_reference(const float* x, int B, int D, float* gram, void* workspace, size_t workspace_bytes,

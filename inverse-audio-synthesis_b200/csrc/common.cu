@@ -21,7 +21,8 @@ constexpr int PROF_RING = 8192;
 const char* const kNames[K_COUNT] = {"k_seed_params", "k_voice_control", "k_voice_audio", "k_pqmf_analysis",
                                      "k_pqmf_synthesis", "k_vicreg_colsum", "k_vicreg_center_pack", "k_vicreg_gram_tc",
                                      "k_vicreg_cov_reduce", "k_vicreg_finalize", "k_vicreg_gram_simt", "k_vicreg_backward",
-                                     "k_abs_avg_pool", "k_voice_schedule", "k_voice_adsr", "k_pool_finalize"};
+                                     "k_abs_avg_pool", "k_voice_schedule", "k_voice_adsr", "k_pool_finalize",
+                                     "k_vicreg_stats_publish", "k_vicreg_stats_combine"};
 struct Prof {
   bool on = false;
   long long launches[K_COUNT] = {0};

@@ -17,7 +17,8 @@ inline cudaStream_t as_stream(ias_stream_t s) { return reinterpret_cast<cudaStre
 // Kernel ids of the launch counter / event profiler (ias_prof_*).
 enum KernelId {
   K_SEED_PARAMS = 0, K_VOICE_CONTROL, K_VOICE_AUDIO, K_PQMF_ANALYSIS, K_PQMF_SYNTHESIS, K_VICREG_COLSUM,
-  K_VICREG_PACK, K_VICREG_GRAM_TC, K_VICREG_COV_REDUCE, K_VICREG_FINALIZE, K_VICREG_GRAM_SIMT, K_VICREG_BWD, K_ABS_AVG_POOL, K_VOICE_SCHEDULE, K_VOICE_ADSR, K_POOL_FINALIZE, K_COUNT
+  K_VICREG_PACK, K_VICREG_GRAM_TC, K_VICREG_COV_REDUCE, K_VICREG_FINALIZE, K_VICREG_GRAM_SIMT, K_VICREG_BWD, K_ABS_AVG_POOL, K_VOICE_SCHEDULE, K_VOICE_ADSR, K_POOL_FINALIZE,
+  K_VICREG_STATS_PUBLISH, K_VICREG_STATS_COMBINE, K_COUNT
 };
 
 // RAII bracket around one kernel launch: always counts it; when profiling is on also records a CUDA event pair on

@@ -14,8 +14,10 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
+#include <vector>
 
 namespace ias {
 namespace {
@@ -1033,6 +1035,51 @@ extern "C" int ias_pqmf_out_len(int T, int N, int K) {
 }
 
 namespace {
+// The cosine-modulated kernels rebuild (part of) the modulation from PQMF.__init__'s formula (pqmf.py:18-30: centre
+// (taps-1)/2, phase (-1)^k pi/4) instead of reading it from the caller, so a caller-supplied factorisation is only
+// honoured when it reproduces the filter that is actually passed: F[k][j] == proto[j] * cos(theta_kj +- phase_k) to
+// fp32 rounding (and, for the small-N analysis kernel that does read mod_host, F[k][j] == proto[j] * mod[k][j % 2N]).
+// Anything else -- e.g. the textbook taps/2 centring -- silently falls back to the direct form, which is valid for
+// any taps.  The last accepted (F, proto, mod) per N and direction is cached, so steady-state calls cost a memcmp.
+struct CmCheck {
+  bool valid = false, ok = false;
+  std::vector<float> F, proto, mod;
+};
+bool cm_design_matches(const float* F_host, const float* proto_host, const float* mod_host, int N, int K,
+                       bool synthesis) {
+  if (!F_host || !proto_host || N > 16 || N < 1) return false;
+  static thread_local CmCheck cache[2][17];
+  CmCheck& c = cache[synthesis ? 1 : 0][N];
+  const size_t nF = (size_t)N * K, nM = mod_host ? (size_t)N * 2 * N : 0;
+  if (c.valid && c.F.size() == nF && c.proto.size() == (size_t)K && c.mod.size() == nM &&
+      memcmp(c.F.data(), F_host, nF * sizeof(float)) == 0 &&
+      memcmp(c.proto.data(), proto_host, K * sizeof(float)) == 0 &&
+      (nM == 0 || memcmp(c.mod.data(), mod_host, nM * sizeof(float)) == 0))
+    return c.ok;
+  const double PI = 3.14159265358979323846;
+  float fmax = 0.0f;
+  for (size_t i = 0; i < nF; ++i) fmax = fmaxf(fmax, fabsf(F_host[i]));
+  const double tol = 2e-6 * (fmax > 0.0f ? fmax : 1.0f);
+  bool ok = true;
+  for (int k = 0; k < N && ok; ++k)
+    for (int j = 0; j < K && ok; ++j) {
+      const double sgn = ((j / (2 * N)) % 2 == 0) ? 1.0 : -1.0;  // the prototype carries the period-2N sign flip
+      const double phase = ((k & 1) ? -1.0 : 1.0) * PI / 4.0;
+      const double theta = (2.0 * k + 1.0) * (PI / (2.0 * N)) * (j - (K - 2) / 2.0);
+      const double want = sgn * (double)proto_host[j] * cos(theta + (synthesis ? -phase : phase));
+      if (fabs(want - (double)F_host[(size_t)k * K + j]) > tol) ok = false;
+      if (ok && mod_host &&
+          fabs((double)proto_host[j] * (double)mod_host[(size_t)k * 2 * N + j % (2 * N)] - (double)F_host[(size_t)k * K + j]) > tol)
+        ok = false;
+    }
+  c.F.assign(F_host, F_host + nF);
+  c.proto.assign(proto_host, proto_host + K);
+  if (mod_host) c.mod.assign(mod_host, mod_host + nM); else c.mod.clear();
+  c.valid = true;
+  c.ok = ok;
+  return ok;
+}
+
 int analysis_entry(const float* x, const float* H_dev, const float* H_host, const float* proto_host,
                    const float* mod_host, const float* row_scale, const float* mean_host, const float* std_host,
                    const float* norm_dev, float* out, int B, int T, int N, int K, ias_stream_t stream, const char* who,
@@ -1043,6 +1090,8 @@ int analysis_entry(const float* x, const float* H_dev, const float* H_host, cons
   const int L = ias_pqmf_out_len(T, N, K);
   IAS_REQUIRE(L > 0, IAS_ERR_INVALID, "%s: empty output (T=%d K=%d)", who, T, K);
   cudaStream_t st = as_stream(stream);
+  if (proto_host && mod_host && !cm_design_matches(H_host, proto_host, mod_host, N, K, false))
+    proto_host = mod_host = nullptr;  // not the PQMF.__init__ design: direct form
   if (H_host && K == 63) {
 #define IAS_PQ(NN, QQ) \
   case NN: return launch_analysis<NN, 63, QQ>(x, H_host, proto_host, mod_host, row_scale, mean_host, std_host, out, B, T, L, st, pr);
@@ -1115,6 +1164,7 @@ extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const floa
   cudaStream_t st = as_stream(stream);
   int q_env = 0;  // IAS_PQMF_SYNTH_Q: tuning override of the time steps per thread
   if (const char* e = getenv("IAS_PQMF_SYNTH_Q")) q_env = atoi(e);
+  if (proto_host && !cm_design_matches(G_host, proto_host, nullptr, N, K, true)) proto_host = nullptr;
   if (proto_host && K == 63) {  // G is the designed filter: cosine-modulated form
     if (N == 16) return launch_synthesis_cm<16, 63>(z, proto_host, y, B, L, st);
     if (N == 8) return launch_synthesis_cm<8, 63>(z, proto_host, y, B, L, st);

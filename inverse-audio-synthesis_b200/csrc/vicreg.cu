@@ -565,6 +565,7 @@ struct BwdArgs {
   float* gx;
   float* gy;
   int B, D, Dp, DT, MT, local_row0, B_local, cfgB, embeddim;
+  int Bstat;      // rows behind the batch statistics (== B, or the global batch when x/y hold one rank's rows only)
   int mt0;        // first row tile computed (MT tiles from there)
   int out_row0;   // gx/gy hold rows [out_row0, out_row0 + out_rows) of the batch
   int out_rows;
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(128, 1) k_bwd_tc(BwdArgs a) {
   const bool local = row >= a.local_row0 && row < a.local_row0 + a.B_local;
   float c_r = local ? (g0 * a.sim + g1) * 2.0f / ((float)a.B_local * (float)a.D) : 0.0f;
   if (s) c_r = -c_r;
-  const float s_scale = -a.gscale * c_std / (2.0f * (float)a.D * (float)(a.B - 1));
+  const float s_scale = -a.gscale * c_std / (2.0f * (float)a.D * (float)(a.Bstat - 1));
   const float kap = kappa * a.gscale;
   float* dst = s ? a.gy : a.gx;
 #pragma unroll
@@ -702,6 +703,7 @@ struct FinalArgs {
   float* out4;
   int P, NV, ncovp_per_side, D, Dp, B, B_local, cfgB, embeddim;
   float sim, stdc, covc;
+  int* epoch;          // statistics exchange: step counter advanced once the step's results are final (else null)
 };
 
 constexpr int FIN_THREADS = 1024;
@@ -776,6 +778,192 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(FinalArgs a) {
     a.out4[1] = repr_loss;
     a.out4[2] = std_loss;
     a.out4[3] = cov_loss;
+    if (a.epoch) *a.epoch += 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Statistics exchange (multi-GPU): instead of gathering the [B_local, D] embeddings and recomputing the
+// global statistics on every rank, each rank reduces its own rows with the single-GPU kernels above (local mean,
+// locally-centred second moments and Gram) and sends that summary -- a `packet` of 4*Dp + 2*ntiles*128*128 floats,
+// 0.39 MB at D = 256 -- to every peer.  The global statistics follow from the exact pooled formulas
+//     mu = sum_q B_q mu_q / B,    G = sum_q [ G_q + B_q (mu_q - mu)(mu_q - mu)^T ],    m2 likewise on the diagonal,
+// which add a small between-rank term to well-conditioned within-rank sums (no X^T X - B mu mu^T cancellation).
+//
+// Transport: one peer-mapped buffer per rank (e.g. torch symmetric memory) laid out as
+//     [ header: int flags[MAX_PEERS] | int epoch @32 | int done @33 ]  (1 KiB)   [ inbox[world][2][packet] ]
+// k_stats_publish (rank r, step e) stores its packet into inbox[r][e & 1] of EVERY rank with plain 16-byte stores over
+// NVLink, then -- last CTA done, after a system-scope fence -- writes e into flags[r] of every rank.
+// k_stats_combine waits until flags[q] >= e for every q (bounded spin, trap on timeout), then reads only its own
+// memory.  No separate barrier or collective launch; double-buffered by the parity of e, so a rank can only overwrite
+// inbox[r][e & 1] at step e + 2, which it reaches after its own combine of step e + 1 saw every peer's flag e + 1,
+// i.e. after every peer finished reading step e (stream order).  k_finalize advances the epoch.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int XCHG_HDR_FLOATS = 256;
+constexpr int XCHG_EPOCH = 32, XCHG_DONE = 33;
+
+__host__ __device__ inline size_t packet_floats(int Dp, int ntiles) {
+  return ((size_t)4 * Dp + (size_t)2 * ntiles * TILE * TILE + 255) / 256 * 256;
+}
+
+struct PeerTable {
+  float* base[MAX_PEERS];
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// grid = any (grid-stride over float4 items of the packet), block = 256
+__global__ void __launch_bounds__(256) k_stats_publish(const float* __restrict__ gram_partial,
+                                                       const float* __restrict__ varpart,
+                                                       const float* __restrict__ mean, int D, int Dp, int ntiles,
+                                                       int splits, int NV, PeerTable peers, int world, int rank) {
+  float* own = peers.base[rank];
+  const int epoch = *reinterpret_cast<const int*>(own + XCHG_EPOCH);  // advanced by k_finalize after this step
+  const size_t pf = packet_floats(Dp, ntiles);
+  const size_t slot = XCHG_HDR_FLOATS + ((size_t)rank * 2 + (epoch & 1)) * pf;
+  const int n4 = (int)(pf / 4);
+  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+    const int f = i4 * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f < 2 * Dp) {  // local column means, [2][Dp]
+      const int s = f / Dp, d = f - s * Dp;
+      float t[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) t[e] = (d + e < D) ? mean[s * D + d + e] : 0.0f;
+      v = make_float4(t[0], t[1], t[2], t[3]);
+    } else if (f < 4 * Dp) {  // locally-centred second moments, [2][Dp]: sum of the NV k_center_pack partials
+      const int g = f - 2 * Dp, s = g / Dp, d = g - s * Dp;
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int p = 0; p < NV; ++p)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (d + e < D) t[e] += varpart[((size_t)p * 2 + s) * D + d + e];
+      v = make_float4(t[0], t[1], t[2], t[3]);
+    } else if ((size_t)f < (size_t)4 * Dp + (size_t)2 * ntiles * TILE * TILE) {  // Gram tiles, K-split partials summed
+      const size_t g = (size_t)f - 4 * Dp;
+      const size_t st = g / (TILE * TILE), e = g - st * (TILE * TILE);  // st = s * ntiles + t
+      const float4* src = reinterpret_cast<const float4*>(gram_partial + st * splits * TILE * TILE + e);
+      int k = 0;
+      for (; k + 4 <= splits; k += 4) {  // four partial tiles in flight
+        const float4 a0 = src[(size_t)(k + 0) * (TILE * TILE / 4)], a1 = src[(size_t)(k + 1) * (TILE * TILE / 4)];
+        const float4 a2 = src[(size_t)(k + 2) * (TILE * TILE / 4)], a3 = src[(size_t)(k + 3) * (TILE * TILE / 4)];
+        v.x += a0.x; v.y += a0.y; v.z += a0.z; v.w += a0.w;
+        v.x += a1.x; v.y += a1.y; v.z += a1.z; v.w += a1.w;
+        v.x += a2.x; v.y += a2.y; v.z += a2.z; v.w += a2.w;
+        v.x += a3.x; v.y += a3.y; v.z += a3.z; v.w += a3.w;
+      }
+      for (; k < splits; ++k) {
+        const float4 a = src[(size_t)k * (TILE * TILE / 4)];
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+      }
+    }
+    for (int q = 0; q < world; ++q) *reinterpret_cast<float4*>(peers.base[q] + slot + f) = v;
+  }
+  // last CTA done: every CTA's packet stores are ordered before its arrival, the last arrival publishes the flag
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* done = reinterpret_cast<int*>(own + XCHG_DONE);
+    if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      for (int q = 0; q < world; ++q) st_release_sys(reinterpret_cast<int*>(peers.base[q]) + rank, epoch);
+    }
+  }
+}
+
+// grid = 2 * ntiles * (TILE / COV_ROWS), block = 256: COV_ROWS rows x 128 cols of one Gram tile (as k_cov_reduce).
+__global__ void __launch_bounds__(256) k_stats_combine(const float* __restrict__ own, int world, int rows_per_rank,
+                                                       int D, int Dp, int DT, int ntiles, float* __restrict__ covp,
+                                                       float* __restrict__ gram_full, float* __restrict__ mean_out,
+                                                       float* __restrict__ m2_out) {
+  __shared__ float s_red[8];
+  extern __shared__ float s_dev[];  // [world][TILE] column deviations, then [world][COV_ROWS] row deviations
+  float (*s_dcol)[TILE] = reinterpret_cast<float (*)[TILE]>(s_dev);
+  float (*s_drow)[COV_ROWS] = reinterpret_cast<float (*)[COV_ROWS]>(s_dev + world * TILE);
+  const int epoch = *reinterpret_cast<const int*>(own + XCHG_EPOCH);
+  if ((int)threadIdx.x < world) {  // wait for every rank's packet of this step (bounded: a lost peer traps, no hang)
+    const int* flag = reinterpret_cast<const int*>(own) + threadIdx.x;
+    unsigned spin = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_sys(flag) < epoch) {
+      if ((++spin & 1023u) == 0) {  // ranks may be seconds apart on their first step (module loading): 30 s budget
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 30000000000ull) __trap();
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  int u = blockIdx.x;
+  const int rb = u % (TILE / COV_ROWS);
+  u /= (TILE / COV_ROWS);
+  const int t = u % ntiles;
+  const int s = u / ntiles;
+  int tm = 0, rem = t;
+  while (rem >= DT - tm) {
+    rem -= DT - tm;
+    ++tm;
+  }
+  const int tn = tm + rem;
+  const size_t pf = packet_floats(Dp, ntiles);
+  const float* inbox = own + XCHG_HDR_FLOATS + (size_t)(epoch & 1) * pf;  // + q * 2 * pf for rank q
+  const float Bl = (float)rows_per_rank, invW = 1.0f / (float)world;
+  // between-rank deviations of the column means for this block's 128 columns and COV_ROWS rows.  Peers wrote the
+  // inbox over NVLink: read it through L2 (ld.cg), never through this SM's L1.
+  if (threadIdx.x < TILE + COV_ROWS) {
+    const int d = threadIdx.x < TILE ? tn * TILE + threadIdx.x : tm * TILE + rb * COV_ROWS + (threadIdx.x - TILE);
+    float m[MAX_PEERS], mu = 0.0f;
+    for (int q = 0; q < world; ++q) {
+      m[q] = __ldcg(inbox + (size_t)q * 2 * pf + (size_t)s * Dp + d);
+      mu += m[q];
+    }
+    mu *= invW;
+    for (int q = 0; q < world; ++q) {
+      if (threadIdx.x < TILE) s_dcol[q][threadIdx.x] = m[q] - mu;
+      else s_drow[q][threadIdx.x - TILE] = m[q] - mu;
+    }
+    if (threadIdx.x < TILE && tm == tn && rb == 0 && d < D) {  // one block per (side, diagonal tile) also emits these
+      float m2 = 0.0f;
+      for (int q = 0; q < world; ++q) {
+        const float dq = m[q] - mu;
+        m2 += __ldcg(inbox + (size_t)q * 2 * pf + 2 * Dp + (size_t)s * Dp + d) + Bl * dq * dq;
+      }
+      mean_out[s * D + d] = mu;
+      m2_out[s * D + d] = m2;
+    }
+  }
+  __syncthreads();
+  float sq = 0.0f;
+  for (int e = threadIdx.x; e < COV_ROWS * TILE; e += 256) {
+    const int rl = e / TILE, c = e % TILE;
+    const int r = rb * COV_ROWS + rl;
+    const size_t off = (size_t)4 * Dp + ((size_t)s * ntiles + t) * (TILE * TILE) + (size_t)r * TILE + c;
+    float g = 0.0f;
+    for (int q = 0; q < world; ++q) g += __ldcg(inbox + (size_t)q * 2 * pf + off) + Bl * s_drow[q][rl] * s_dcol[q][c];
+    const int gi = tm * TILE + r, gj = tn * TILE + c;
+    if (gi != gj) sq = fmaf(g, g, sq);
+    gram_full[((size_t)s * Dp + gi) * Dp + gj] = g;
+    if (tm != tn) gram_full[((size_t)s * Dp + gj) * Dp + gi] = g;
+  }
+  if (tm != tn) sq *= 2.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.0f;
+    for (int w = 0; w < 8; ++w) tsum += s_red[w];
+    covp[blockIdx.x] = tsum;
   }
 }
 
@@ -881,6 +1069,7 @@ extern "C" int ias_vicreg_loss(const float* x, const float* y, int B, int local_
   a.ncovp_per_side = p.ntiles * (TILE / COV_ROWS);
   a.D = D; a.Dp = p.Dp; a.B = B; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
   a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
+  a.epoch = nullptr;
   {
     ProfScope prof_(K_VICREG_FINALIZE, st);
     k_finalize<<<1, FIN_THREADS, 0, st>>>(a);
@@ -927,7 +1116,7 @@ namespace ias {
 namespace {
 int run_backward(const float* x, const float* y, const Plan& p, int local_row0, int B_local, int cfgB, int embeddim,
                  float sim, float stdc, float covc, const float* gout4, float* gx, float* gy, int out_row0, int out_rows,
-                 float gscale, float* w, cudaStream_t st) {
+                 float gscale, float* w, cudaStream_t st, int Bstat = 0) {
   const int mt0 = out_row0 / TILE;
   const int mt1 = (out_row0 + out_rows + TILE - 1) / TILE;
   const int MTn = mt1 - mt0;
@@ -957,6 +1146,7 @@ int run_backward(const float* x, const float* y, const Plan& p, int local_row0, 
   a.B = p.B; a.D = p.D; a.Dp = p.Dp; a.DT = p.DT; a.MT = MTn;
   a.local_row0 = local_row0; a.B_local = B_local; a.cfgB = cfgB; a.embeddim = embeddim;
   a.mt0 = mt0; a.out_row0 = out_row0; a.out_rows = out_rows; a.gscale = gscale;
+  a.Bstat = Bstat > 0 ? Bstat : p.B;
   a.sim = sim; a.stdc = stdc; a.covc = covc;
   {
     ProfScope prof_(K_VICREG_BWD, st);
@@ -1040,6 +1230,7 @@ extern "C" int ias_vicreg_loss_gather(const float* const* x_peers_host, const fl
   a.ncovp_per_side = p.ntiles * (TILE / COV_ROWS);
   a.D = D; a.Dp = p.Dp; a.B = p.B; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
   a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
+  a.epoch = nullptr;
   {
     ProfScope prof_(K_VICREG_FINALIZE, st);
     k_finalize<<<1, FIN_THREADS, 0, st>>>(a);
@@ -1065,4 +1256,107 @@ extern "C" int ias_vicreg_loss_gather_backward(int world, int rank, int B_local,
   // `world` times the own-row slice: no reduce-scatter is needed (FullGatherLayer.backward semantics, vicreg.py:92-95).
   return run_backward(w + off_xg, w + off_yg, p, rank * B_local, B_local, cfg_batch_size, embeddim, sim_coeff, std_coeff,
                       cov_coeff, gout4, gx_local, gy_local, rank * B_local, B_local, (float)world, w, as_stream(stream));
+}
+
+// ---- statistics exchange path ---------------------------------------------------------------------------------------
+extern "C" size_t ias_vicreg_stats_buffer_bytes(int world, int D) {
+  if (world <= 0 || D <= 0) return 0;
+  const Plan p = make_plan(TILE, D);
+  return ((size_t)XCHG_HDR_FLOATS + (size_t)world * 2 * packet_floats(p.Dp, p.ntiles)) * sizeof(float);
+}
+
+extern "C" int ias_vicreg_loss_stats(const float* x, const float* y, float* const* buffers_host, int world, int rank,
+                                     int B_local, int cfg_batch_size, int D, int embeddim, float sim_coeff,
+                                     float std_coeff, float cov_coeff, float* out4, void* workspace,
+                                     size_t workspace_bytes, ias_stream_t stream) {
+  int rc = check_common(x, B_local, D, workspace, workspace_bytes, "ias_vicreg_loss_stats");
+  if (rc) return rc;
+  IAS_REQUIRE(y && out4 && buffers_host, IAS_ERR_INVALID, "ias_vicreg_loss_stats: NULL pointer");
+  IAS_REQUIRE(world >= 1 && world <= MAX_PEERS && rank >= 0 && rank < world, IAS_ERR_INVALID,
+              "ias_vicreg_loss_stats: world=%d rank=%d (at most %d peers)", world, rank, MAX_PEERS);
+  IAS_REQUIRE(cfg_batch_size != 1 && embeddim > 0 && (long long)world * B_local > 1, IAS_ERR_INVALID,
+              "ias_vicreg_loss_stats: cfg_batch_size=%d embeddim=%d", cfg_batch_size, embeddim);
+  const Plan p = make_plan(B_local, D);
+  PeerTable peers;
+  for (int i = 0; i < MAX_PEERS; ++i) peers.base[i] = nullptr;
+  for (int i = 0; i < world; ++i) {
+    IAS_REQUIRE(buffers_host[i] && ias_aligned16(buffers_host[i]), IAS_ERR_INVALID,
+                "ias_vicreg_loss_stats: peer buffer %d is NULL or not 16-byte aligned", i);
+    peers.base[i] = buffers_host[i];
+  }
+  float* w = reinterpret_cast<float*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  // local rows -> local mean, centred second moments, K-split Gram partials (the single-GPU kernels, B = B_local)
+  {
+    bool v4 = (p.D % 4 == 0) && ias_aligned16(x) && ias_aligned16(y);
+    ProfScope prof_(K_VICREG_COLSUM, st);
+    if (v4)
+      k_colsum_v4<<<p.P, CS_THREADS, 0, st>>>(single_src(x, y, B_local), p.B, p.D, 0, B_local, w + p.off_partial,
+                                              w + p.off_repr, nullptr, nullptr);
+    else
+      k_colsum<<<p.P, 256, 0, st>>>(single_src(x, y, B_local), p.B, p.D, 0, B_local, w + p.off_partial, w + p.off_repr,
+                                    nullptr, nullptr);
+  }
+  IAS_LAUNCH_CHECK("k_colsum");
+  {
+    ProfScope prof_(K_VICREG_PACK, st);
+    k_center_pack<<<dim3(p.NV, 2), 256, 0, st>>>(x, y, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
+                                                w + p.off_varpart, w + p.off_packed);
+  }
+  IAS_LAUNCH_CHECK("k_center_pack");
+  rc = launch_gram(p, w, st);
+  if (rc) return rc;
+  const size_t pf = packet_floats(p.Dp, p.ntiles);
+  {
+    ProfScope prof_(K_VICREG_STATS_PUBLISH, st);
+    const int grid = (int)((pf / 4 + 255) / 256);
+    k_stats_publish<<<grid, 256, 0, st>>>(w + p.off_gram, w + p.off_varpart, w + p.off_mean, D, p.Dp, p.ntiles, p.splits,
+                                          p.NV, peers, world, rank);
+  }
+  IAS_LAUNCH_CHECK("k_stats_publish");
+  {
+    // the combine overwrites the local mean with the global one and leaves the global centred second moments where
+    // k_finalize reads variance partials (as a single partial)
+    ProfScope prof_(K_VICREG_STATS_COMBINE, st);
+    k_stats_combine<<<2 * p.ntiles * (TILE / COV_ROWS), 256, (size_t)world * (TILE + COV_ROWS) * sizeof(float), st>>>(peers.base[rank], world, B_local, D, p.Dp, p.DT,
+                                                                   p.ntiles, w + p.off_covp, w + p.off_gfull,
+                                                                   w + p.off_mean, w + p.off_varpart);
+  }
+  IAS_LAUNCH_CHECK("k_stats_combine");
+  FinalArgs a;
+  a.repr = w + p.off_repr;
+  a.covp = w + p.off_covp;
+  a.varpart = w + p.off_varpart;
+  a.stats = w + p.off_stats;
+  a.out4 = out4;
+  a.P = p.P;
+  a.NV = 1;
+  a.ncovp_per_side = p.ntiles * (TILE / COV_ROWS);
+  a.D = D; a.Dp = p.Dp; a.B = world * B_local; a.B_local = B_local; a.cfgB = cfg_batch_size; a.embeddim = embeddim;
+  a.sim = sim_coeff; a.stdc = std_coeff; a.covc = cov_coeff;
+  a.epoch = reinterpret_cast<int*>(peers.base[rank] + XCHG_EPOCH);
+  {
+    ProfScope prof_(K_VICREG_FINALIZE, st);
+    k_finalize<<<1, FIN_THREADS, 0, st>>>(a);
+  }
+  IAS_LAUNCH_CHECK("k_finalize");
+  return IAS_OK;
+}
+
+extern "C" int ias_vicreg_loss_stats_backward(const float* x, const float* y, int world, int B_local,
+                                              int cfg_batch_size, int D, int embeddim, float sim_coeff,
+                                              float std_coeff, float cov_coeff, const float* gout4, float* gx_local,
+                                              float* gy_local, void* workspace, size_t workspace_bytes,
+                                              ias_stream_t stream) {
+  int rc = check_common(x, B_local, D, workspace, workspace_bytes, "ias_vicreg_loss_stats_backward");
+  if (rc) return rc;
+  IAS_REQUIRE(y && gout4 && gx_local && gy_local, IAS_ERR_INVALID, "ias_vicreg_loss_stats_backward: NULL pointer");
+  IAS_REQUIRE(world >= 1 && (long long)world * B_local > 1 && cfg_batch_size != 1 && embeddim > 0, IAS_ERR_INVALID,
+              "ias_vicreg_loss_stats_backward: world=%d B_local=%d cfg_batch_size=%d", world, B_local, cfg_batch_size);
+  const Plan p = make_plan(B_local, D);
+  // every rank holds the same std/cov terms: the sum over ranks of their gradients w.r.t. this rank's rows is `world`
+  // times the own-row slice (FullGatherLayer.backward semantics, vicreg.py:92-95) -- no communication
+  return run_backward(x, y, p, 0, B_local, cfg_batch_size, embeddim, sim_coeff, std_coeff, cov_coeff, gout4, gx_local,
+                      gy_local, 0, B_local, (float)world, reinterpret_cast<float*>(workspace), as_stream(stream),
+                      world * B_local);
 }

@@ -713,6 +713,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
       }
       // ---- pass 2: oscillators, VCA gains, noise, mix --------------------------------------------------------
       float y[SPT];
+      float lpeak = 0.0f;  // peak of this thread's samples of this tile (VEC: merged below only if the thread is live)
 #pragma unroll
       for (int k = 0; k < SPT; k += 2) {
         const P2 sp = p2(srcs[k], srcs[k + 1]);
@@ -736,8 +737,8 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
                              p2_fma(squaresaw_core_p2(arg2, pk, shape), g2, p2_mul(p2(nzv[k], nzv[k + 1]), g3)));
         y[k] = p2lo(yy);
         y[k + 1] = p2hi(yy);
-        if (VEC || (t0 + k) < T) tpeak = fmaxf(tpeak, fabsf(y[k]));
-        if (VEC || (t0 + k + 1) < T) tpeak = fmaxf(tpeak, fabsf(y[k + 1]));
+        if (VEC || (t0 + k) < T) lpeak = fmaxf(lpeak, fabsf(y[k]));
+        if (VEC || (t0 + k + 1) < T) lpeak = fmaxf(lpeak, fabsf(y[k + 1]));
         if (DBG) {
           if ((t0 + k) < T) {
             A.phase_dbg[((size_t)b * 2 + 0) * T + t0 + k] = p2lo(arg1);
@@ -749,6 +750,10 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
           }
         }
       }
+      // VEC: T % SPT == 0, so a thread is wholly live or wholly past the end of the clip.  Threads past the end of
+      // the last tile still ran both passes (phase keeps accumulating, gains stay at the last control point): their
+      // samples do not exist in the reference and must not reach max|mixed|.
+      if (!VEC || t0 < T) tpeak = fmaxf(tpeak, lpeak);
       if (VEC) {
         if (t0 < T) {
 #pragma unroll

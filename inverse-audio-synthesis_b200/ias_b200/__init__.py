@@ -8,7 +8,7 @@ The package contains no arithmetic of its own and no fallback path: every call g
 (hand-written sm_100a kernels) and raises if the library or a CUDA device is missing.
 """
 from ._lib import IasError, build, lib  # noqa: F401
-from .dist import Communicator, EmbeddingExchange, use_communicator, use_fused_gather  # noqa: F401
+from .dist import Communicator, EmbeddingExchange, StatsExchange, use_communicator, use_fused_gather  # noqa: F401
 from .pqmf import PQMF  # noqa: F401
 from .vicreg import FullGatherLayer, Projector, VICReg, exclude_bias_and_norm, off_diagonal, vicreg_loss  # noqa: F401
 from .voice import ModuleParameter, ModuleParameterRange, SynthConfig, Voice  # noqa: F401

@@ -17,6 +17,7 @@ COMM_LIB_PATH = os.path.join(_HERE, "libias_comm.so")
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 IAS_OK = 0
+IAS_ERR_INVALID, IAS_ERR_CUDA, IAS_ERR_UNSUPPORTED, IAS_ERR_WORKSPACE, IAS_ERR_NCCL = 1, 2, 3, 4, 5
 NPARAMS = 78
 NCONTROL = 5
 
@@ -25,7 +26,12 @@ _comm = None
 
 
 class IasError(RuntimeError):
-    pass
+    """Raised for every failed library call; ``code`` is the IAS_ERR_* value the C ABI returned (None when the error
+    was detected on the Python side)."""
+
+    def __init__(self, message: str, code=None):
+        super().__init__(message)
+        self.code = code
 
 
 def build(verbose: bool = False) -> None:
@@ -94,6 +100,17 @@ _SIGNATURES = {
         [c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
          c_size_t, c_void_p],
     ),
+    "ias_vicreg_stats_buffer_bytes": (c_size_t, [c_int, c_int]),
+    "ias_vicreg_loss_stats": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p,
+         c_void_p, c_size_t, c_void_p],
+    ),
+    "ias_vicreg_loss_stats_backward": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_size_t, c_void_p],
+    ),
     "ias_vicreg_gram_reference": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ias_vicreg_gram_tc": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ias_pqmf_pool_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
@@ -152,13 +169,13 @@ def comm_lib() -> ctypes.CDLL:
 def check(rc: int, what: str = "") -> None:
     if rc != IAS_OK:
         msg = lib().ias_last_error().decode("utf-8", "replace")
-        raise IasError(f"{what or 'libias_b200'} failed (code {rc}): {msg}")
+        raise IasError(f"{what or 'libias_b200'} failed (code {rc}): {msg}", code=rc)
 
 
 def check_comm(rc: int, what: str = "") -> None:
     if rc != IAS_OK:
         msg = comm_lib().ias_comm_last_error().decode("utf-8", "replace")
-        raise IasError(f"{what or 'libias_comm'} failed (code {rc}): {msg}")
+        raise IasError(f"{what or 'libias_comm'} failed (code {rc}): {msg}", code=rc)
 
 
 def ptr(t) -> c_void_p:

@@ -1,4 +1,10 @@
-"""Process-group plumbing for the one collective of the hot path: the all-gather of the embeddings.
+"""Process-group plumbing for the one exchange step of the hot path: what the loss needs from the other
+ranks' embeddings.  Three routes, same result as the single-process loss on the rank-ordered concatenation:
+
+  * ``StatsExchange`` + ``FusedStatsLoss`` (default of bench.py): every rank reduces its own rows and pushes a 0.4 MB
+    summary (mean, centred second moments, Gram) to its peers over NVLink from inside the loss kernels; no collective;
+  * ``EmbeddingExchange`` + ``FusedGatherLoss``: the statistics kernel reads every peer's embeddings over NVLink;
+  * ``FullGatherLayer`` (vicreg.py): an NCCL all-gather through torch.distributed or ``Communicator`` below.
 
 ``Communicator`` owns an NCCL communicator created through the C ABI (``ias_comm_*`` in libias_comm.so); the unique id
 is made on rank 0 and handed to the other ranks with ``torch.distributed.broadcast_object_list`` (any initialised
@@ -14,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .vicreg import aligned_workspace, needs_backward
 
 _active: Optional["Communicator"] = None
 
@@ -114,13 +121,50 @@ class EmbeddingExchange:
         return self.workspace
 
 
-def use_fused_gather(exchange: Optional[EmbeddingExchange]) -> None:
-    """Route VICReg.loss through the fused gather kernels (None: back to FullGatherLayer + ias_vicreg_loss)."""
+class StatsExchange:
+    """Peer-visible inbox of this rank for the statistics exchange (``ias_vicreg_loss_stats``): one symmetric-memory
+    block per rank holding a 1 KiB header (arrival flags, step counter) and ``world`` x 2 summary slots.  Allocation and
+    the address exchange go through torch symmetric memory; every byte that moves afterwards is written by the loss
+    kernels themselves."""
+
+    def __init__(self, D: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise _lib.IasError("StatsExchange needs an initialised torch.distributed process group")
+        group = group if group is not None else dist.group.WORLD
+        self.D, self.device = int(D), torch.device(device)
+        world = dist.get_world_size(group)
+        nbytes = _lib.lib().ias_vicreg_stats_buffer_bytes(world, self.D)
+        self.buf = symm.empty((nbytes // 4,), dtype=torch.float32, device=self.device)
+        self.buf.zero_()
+        self.buf.view(torch.int32)[32] = 1  # step counter (ias_b200.h: the int at byte offset 128 starts at 1)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.world, self.rank = int(self.hdl.world_size), int(self.hdl.rank)
+        self.ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)  # nobody pushes into an inbox that is still being zeroed
+        self._scratch = None
+
+    def ws(self, b_local: int) -> torch.Tensor:
+        need = _lib.lib().ias_vicreg_workspace_bytes(b_local, self.D)
+        if self._scratch is None or self._scratch.numel() * 4 < need:
+            self._scratch = aligned_workspace(need, self.device)
+        return self._scratch
+
+    def step(self) -> int:
+        """Step counter as the device sees it (synchronises; diagnostics only)."""
+        return int(self.buf.view(torch.int32)[32].item())
+
+
+def use_fused_gather(exchange) -> None:
+    """Route VICReg.loss through ``exchange``: a ``StatsExchange`` (summary exchange inside the loss kernels) or an
+    ``EmbeddingExchange`` (peer reads of the embeddings).  None: back to FullGatherLayer + ias_vicreg_loss."""
     global _exchange
     _exchange = exchange
 
 
-def fused_exchange() -> Optional[EmbeddingExchange]:
+def fused_exchange():
     return _exchange
 
 
@@ -134,14 +178,17 @@ class FusedGatherLoss(torch.autograd.Function):
         if tuple(x.shape) != (ex.b_local, ex.D) or tuple(y.shape) != (ex.b_local, ex.D):
             raise _lib.IasError(f"EmbeddingExchange was built for [{ex.b_local},{ex.D}], got {tuple(x.shape)}")
         ex.publish(x.float(), y.float())
-        ws = ex.ws()
+        # a forward that may be differentiated owns its workspace (see vicreg._VicregLossFn)
+        grad = needs_backward(x, y)
+        ws = aligned_workspace(_lib.lib().ias_vicreg_gather_workspace_bytes(ex.world, ex.b_local, ex.D),
+                               x.device) if grad else ex.ws()
         out4 = torch.empty(4, dtype=torch.float32, device=x.device)
         with _lib.on_device(x):
             rc = _lib.lib().ias_vicreg_loss_gather(ex.x_ptrs, ex.y_ptrs, ex.world, ex.rank, ex.b_local, cfg_batch, ex.D,
                                                    embeddim, sim, stdc, covc, _lib.ptr(out4), _lib.ptr(ws),
                                                    ws.numel() * 4, _lib.current_stream(x.device))
         _lib.check(rc, "ias_vicreg_loss_gather")
-        ctx.ex, ctx.args = ex, (cfg_batch, embeddim, sim, stdc, covc)
+        ctx.ex, ctx.args, ctx.ws = ex, (cfg_batch, embeddim, sim, stdc, covc), ws
         return out4[0], out4[1], out4[2], out4[3]
 
     @staticmethod
@@ -152,11 +199,54 @@ class FusedGatherLoss(torch.autograd.Function):
         gout = torch.stack([g if g is not None else zero for g in (g0, g1, g2, g3)]).float().contiguous()
         gx = torch.empty((ex.b_local, ex.D), dtype=torch.float32, device=ex.device)
         gy = torch.empty_like(gx)
-        ws = ex.ws()
+        ws = ctx.ws
         with _lib.on_device(gx):
             rc = _lib.lib().ias_vicreg_loss_gather_backward(ex.world, ex.rank, ex.b_local, cfg_batch, ex.D, embeddim,
                                                             sim, stdc, covc, _lib.ptr(gout), _lib.ptr(gx), _lib.ptr(gy),
                                                             _lib.ptr(ws), ws.numel() * 4,
                                                             _lib.current_stream(ex.device))
         _lib.check(rc, "ias_vicreg_loss_gather_backward")
+        return gx, gy, None, None, None, None, None, None
+
+
+class FusedStatsLoss(torch.autograd.Function):
+    """loss(x_local, y_local) over the global batch through the statistics exchange: forward =
+    ``ias_vicreg_loss_stats``, backward = ``ias_vicreg_loss_stats_backward`` (own rows, no communication)."""
+
+    @staticmethod
+    def forward(ctx, x, y, ex, cfg_batch, embeddim, sim, stdc, covc):
+        _lib.require_cuda(x, "VICReg.loss x")
+        _lib.require_cuda(y, "VICReg.loss y")
+        if x.dim() != 2 or x.shape[1] != ex.D or tuple(y.shape) != tuple(x.shape):
+            raise _lib.IasError(f"StatsExchange was built for D={ex.D}, got x {tuple(x.shape)} y {tuple(y.shape)}")
+        xc = x.detach().to(torch.float32).contiguous()
+        yc = y.detach().to(torch.float32).contiguous()
+        b_local = xc.shape[0]
+        lib = _lib.lib()
+        grad = needs_backward(x, y)
+        ws = aligned_workspace(lib.ias_vicreg_workspace_bytes(b_local, ex.D), xc.device) if grad else ex.ws(b_local)
+        out4 = torch.empty(4, dtype=torch.float32, device=xc.device)
+        with _lib.on_device(xc):
+            rc = lib.ias_vicreg_loss_stats(_lib.ptr(xc), _lib.ptr(yc), ex.ptrs, ex.world, ex.rank, b_local, cfg_batch,
+                                           ex.D, embeddim, sim, stdc, covc, _lib.ptr(out4), _lib.ptr(ws),
+                                           ws.numel() * 4, _lib.current_stream(xc.device))
+        _lib.check(rc, "ias_vicreg_loss_stats")
+        ctx.save_for_backward(xc, yc)
+        ctx.args, ctx.ws, ctx.world = (cfg_batch, ex.D, embeddim, sim, stdc, covc), ws, ex.world
+        return out4[0], out4[1], out4[2], out4[3]
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, g3):
+        xc, yc = ctx.saved_tensors
+        cfg_batch, D, embeddim, sim, stdc, covc = ctx.args
+        zero = torch.zeros((), dtype=torch.float32, device=xc.device)
+        gout = torch.stack([g if g is not None else zero for g in (g0, g1, g2, g3)]).float().contiguous()
+        gx, gy = torch.empty_like(xc), torch.empty_like(yc)
+        ws = ctx.ws
+        with _lib.on_device(xc):
+            rc = _lib.lib().ias_vicreg_loss_stats_backward(_lib.ptr(xc), _lib.ptr(yc), ctx.world, xc.shape[0], cfg_batch,
+                                                           D, embeddim, sim, stdc, covc, _lib.ptr(gout), _lib.ptr(gx),
+                                                           _lib.ptr(gy), _lib.ptr(ws), ws.numel() * 4,
+                                                           _lib.current_stream(xc.device))
+        _lib.check(rc, "ias_vicreg_loss_stats_backward")
         return gx, gy, None, None, None, None, None, None

@@ -86,7 +86,25 @@ class FullGatherLayer(torch.autograd.Function):
         return stacked[ctx.rank]
 
 
+def aligned_workspace(nbytes: int, device) -> torch.Tensor:
+    """float32 scratch of at least ``nbytes`` whose address is 1 KiB aligned (the caching allocator hands out
+    512-byte aligned blocks: over-allocate and slice; the view keeps the block alive)."""
+    raw = torch.empty(nbytes // 4 + 256, dtype=torch.float32, device=device)
+    shift = (-raw.data_ptr() % 1024) // 4
+    return raw[shift:shift + nbytes // 4]
+
+
+def needs_backward(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
 class _VicregLossFn(torch.autograd.Function):
+    """``ias_vicreg_loss`` / ``ias_vicreg_loss_backward``.  The C ABI keeps what the backward needs (column means, std,
+    the full Gram) in the workspace of the forward call "until the next forward call on it" (ias_b200.h).  A forward
+    that may be differentiated therefore gets a workspace of its own, owned by its autograd node, so two ``loss()``
+    calls before the first ``backward()`` -- two view pairs, a diagnostic loss on another batch -- cannot overwrite each
+    other's state; only forwards under ``no_grad`` share the module-wide scratch buffer."""
+
     @staticmethod
     def forward(ctx, x, y, local_row0, b_local, cfg_batch, embeddim, sim, stdc, covc, holder):
         _lib.require_cuda(x, "VICReg.loss x")
@@ -95,7 +113,10 @@ class _VicregLossFn(torch.autograd.Function):
         yc = y.detach().to(torch.float32).contiguous()
         B, D = xc.shape
         lib = _lib.lib()
-        ws = holder.workspace(B, D, xc.device)
+        if needs_backward(x, y):
+            ws = aligned_workspace(lib.ias_vicreg_workspace_bytes(B, D), xc.device)
+        else:
+            ws = holder.workspace(B, D, xc.device)
         out4 = torch.empty(4, dtype=torch.float32, device=xc.device)
         with _lib.on_device(xc):
             rc = lib.ias_vicreg_loss(_lib.ptr(xc), _lib.ptr(yc), B, local_row0, b_local, cfg_batch, D, embeddim, sim,
@@ -104,7 +125,6 @@ class _VicregLossFn(torch.autograd.Function):
         _lib.check(rc, "ias_vicreg_loss")
         ctx.save_for_backward(xc, yc)
         ctx.args = (B, local_row0, b_local, cfg_batch, D, embeddim, sim, stdc, covc)
-        ctx.holder = holder
         ctx.ws = ws
         return out4[0], out4[1], out4[2], out4[3]
 
@@ -127,34 +147,46 @@ class _VicregLossFn(torch.autograd.Function):
 
 
 class _Workspace:
+    """Module-wide scratch for forwards that will not be differentiated."""
+
     def __init__(self):
         self.buf: Optional[torch.Tensor] = None
 
     def workspace(self, B: int, D: int, device) -> torch.Tensor:
         need = _lib.lib().ias_vicreg_workspace_bytes(B, D)
         if self.buf is None or self.buf.device != device or self.buf.numel() * 4 < need:
-            # float32 storage from the caching allocator: 512-byte aligned blocks; over-allocate and slice to 1 KiB
-            raw = torch.empty(need // 4 + 256, dtype=torch.float32, device=device)
-            shift = (-raw.data_ptr() % 1024) // 4
-            self.buf = raw[shift:shift + need // 4]
-            self._raw = raw
+            self.buf = aligned_workspace(need, device)
         return self.buf
 
 
 def vicreg_loss(x, y, cfg_batch_size: int, embeddim: int, sim_coeff: float, std_coeff: float, cov_coeff: float,
-                gather: bool = True, _holder: Optional[_Workspace] = None):
-    """Functional form of ``VICReg.loss`` -> (loss, repr_loss, std_loss, cov_loss), 0-d tensors."""
+                gather: bool = True, _holder: Optional[_Workspace] = None, strict_batch: bool = True):
+    """Functional form of ``VICReg.loss`` -> (loss, repr_loss, std_loss, cov_loss), 0-d tensors.
+
+    ``gather`` (and an initialised process group with world size > 1) makes the variance / covariance terms see the
+    global batch, as the reference intends (vicreg.py:38-39).  ``cfg_batch_size`` is the covariance divisor
+    (vicreg.py:47-48) and must then be the GLOBAL batch size: a per-GPU value would inflate ``cov_loss`` by ~W^2
+    without any other symptom, so a mismatch with ``world * x.shape[0]`` raises unless ``strict_batch=False``."""
     holder = _holder if _holder is not None else _Workspace()
     rank, world = _world()
     b_local = x.shape[0]
     if gather and world > 1:
+        if strict_batch and int(cfg_batch_size) != world * b_local:
+            raise _lib.IasError(
+                f"VICReg.loss gathers the embeddings of {world} ranks ({world} x {b_local} rows) but "
+                f"cfg.vicreg.batch_size = {cfg_batch_size}: with the gather enabled it is the covariance divisor of the "
+                f"GLOBAL batch (vicreg.py:47-48) and must be {world * b_local}; the per-GPU size belongs in "
+                "SynthConfig.batch_size.  Pass gather=False for the reference's per-rank statistics, or "
+                "strict_batch=False to keep this divisor.")
         from . import dist as ias_dist
 
         ex = ias_dist.fused_exchange()
+        if isinstance(ex, ias_dist.StatsExchange):
+            return ias_dist.FusedStatsLoss.apply(x, y, ex, int(cfg_batch_size), int(embeddim), float(sim_coeff),
+                                                 float(std_coeff), float(cov_coeff))
         if ex is not None:
             return ias_dist.FusedGatherLoss.apply(x, y, ex, int(cfg_batch_size), int(embeddim), float(sim_coeff),
                                                   float(std_coeff), float(cov_coeff))
-    if gather and world > 1:
         x_all = torch.cat(FullGatherLayer.apply(x), dim=0)
         y_all = torch.cat(FullGatherLayer.apply(y), dim=0)
         row0 = rank * b_local
@@ -165,7 +197,13 @@ def vicreg_loss(x, y, cfg_batch_size: int, embeddim: int, sim_coeff: float, std_
 
 
 class VICReg(nn.Module):
-    def __init__(self, cfg, backbone_audio: nn.Module, backbone_param: nn.Module, gather: bool = True):
+    def __init__(self, cfg, backbone_audio: nn.Module, backbone_param: nn.Module, gather: bool = True,
+                 strict_batch: bool = True):
+        """``gather``: with an initialised process group of world size > 1, the variance / covariance terms are
+        computed over the global batch (the FullGatherLayer call the reference has commented out at vicreg.py:38-39 and
+        its README calls a bug; BASELINE north star).  ``cfg.vicreg.batch_size`` must then be the global batch size
+        (checked, see ``vicreg_loss``).  ``gather=False`` reproduces the reference as it runs today: per-rank
+        statistics with ``cfg.vicreg.batch_size`` as the divisor."""
         super().__init__()
         self.cfg = cfg
         self.reprdim = cfg.dim
@@ -174,6 +212,7 @@ class VICReg(nn.Module):
         self.backbone_param = backbone_param
         self.projector = Projector(cfg, self.reprdim)
         self.gather = gather
+        self.strict_batch = strict_batch
         self._holder = _Workspace()
 
     def forward(self, audio, params):
@@ -184,7 +223,7 @@ class VICReg(nn.Module):
     def loss(self, x, y):
         v = self.cfg.vicreg
         return vicreg_loss(x, y, v.batch_size, self.embeddim, v.sim_coeff, v.std_coeff, v.cov_coeff,
-                           gather=self.gather, _holder=self._holder)
+                           gather=self.gather, _holder=self._holder, strict_batch=self.strict_batch)
 
 
 def exclude_bias_and_norm(p):

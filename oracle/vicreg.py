@@ -110,3 +110,23 @@ def full_gather_backward(grads_per_rank: Sequence[np.ndarray], rank: int, b_loca
     """Every rank holds a gradient w.r.t. the gathered [W*B_local, D]; all-reduce(sum), keep the own slice."""
     total = np.sum(np.stack(list(grads_per_rank)), axis=0)
     return total[rank * b_local:(rank + 1) * b_local]
+
+
+def pooled_statistics(shards: Sequence[np.ndarray]):
+    """Global column mean, centred second moments and centred Gram of the rank-ordered concatenation, computed from
+    per-rank summaries only -- the algebra of the statistics exchange (``ias_vicreg_loss_stats``), restated in float64:
+
+        mu = sum_q B_q mu_q / B,      G = sum_q [ G_q + B_q (mu_q - mu)(mu_q - mu)^T ],      m2 = diag(G)
+
+    with mu_q, G_q the mean and the locally-centred Gram of rank q's rows.  Equal, up to rounding, to centring the
+    gathered batch as vicreg.py:40-48 does after the (intended) FullGatherLayer call at vicreg.py:38-39."""
+    shards = [np.asarray(s, dtype=np.float64) for s in shards]
+    B = sum(s.shape[0] for s in shards)
+    mus = [s.mean(axis=0) for s in shards]
+    mu = sum(s.shape[0] * m for s, m in zip(shards, mus)) / B
+    G = np.zeros((shards[0].shape[1],) * 2)
+    for s, m in zip(shards, mus):
+        c = s - m
+        d = m - mu
+        G += c.T @ c + s.shape[0] * np.outer(d, d)
+    return mu, np.diag(G).copy(), G

@@ -234,3 +234,38 @@ def test_pooled_epilogue_refuses_shapes_it_cannot_cover(cuda_device):
     m5 = _mod(5, 0.15, cuda_device)  # no specialised kernel
     with pytest.raises(ias_b200.IasError):
         m5.analysis_pooled(x, 16)
+
+
+@pytest.mark.parametrize("N", [3, 16])
+def test_foreign_cosine_modulated_bank_with_stale_factors_takes_the_direct_form(cuda_device, N):
+    """C-ABI callers may pass any filter with a (proto, mod) factorisation.  The fast kernels rebuild the modulation
+    from PQMF.__init__'s design, so a bank they do not describe -- here the textbook taps/2 centring of the reference's
+    own TODO (pqmf.py:26), passed together with the factors of the default design -- must fall back to the direct form
+    instead of silently filtering with the wrong taps (ias_b200.h, ias_pqmf_analysis / ias_pqmf_synthesis)."""
+    import ias_b200
+    from ias_b200 import _lib
+    from ias_b200.pqmf import cosine_modulation_factors
+    from scipy import signal as sig
+
+    taps, K = 62, 63
+    proto = sig.firwin(K, 0.15, window=("kaiser", 9.0))
+    k = np.arange(N)[:, None]
+    j = np.arange(K)[None, :]
+    theta = (2 * k + 1) * (np.pi / (2 * N)) * (j - taps / 2)   # textbook centring, NOT the reference's (taps-1)/2
+    phase = ((-1.0) ** k) * np.pi / 4
+    H = (2 * proto * np.cos(theta + phase)).astype(np.float32)
+    G = (2 * proto * np.cos(theta - phase)).astype(np.float32)
+    g, c = cosine_modulation_factors(N, taps, 0.15, 9.0)        # factors of the DEFAULT design: stale for H, G
+    x = MG.pqmf_input(2, 9000, seed=5).to(cuda_device)
+    lib = ias_b200.lib()
+    L = lib.ias_pqmf_out_len(9000, N, K)
+    Hh, Gh = torch.from_numpy(H).contiguous(), torch.from_numpy(G).contiguous()
+    gh, ch = torch.from_numpy(g).contiguous(), torch.from_numpy(c).contiguous()
+    z = torch.empty((2, N, L), device=cuda_device)
+    _lib.check(lib.ias_pqmf_analysis(_lib.ptr(x), _lib.ptr(Hh.to(cuda_device)), _lib.ptr(Hh), _lib.ptr(gh), _lib.ptr(ch),
+                                     None, _lib.ptr(z), 2, 9000, N, K, _lib.current_stream(cuda_device)))
+    assert OP.rel_err(z.cpu().numpy(), OP.analysis(x.cpu().numpy()[:, 0, :], H.astype(np.float64), N)) <= TOL
+    y = torch.empty((2, L * N), device=cuda_device)
+    _lib.check(lib.ias_pqmf_synthesis(_lib.ptr(z), _lib.ptr(Gh.to(cuda_device)), _lib.ptr(Gh), _lib.ptr(gh), _lib.ptr(y),
+                                      2, L, N, K, _lib.current_stream(cuda_device)))
+    assert OP.rel_err(y.cpu().numpy(), OP.synthesis(z.cpu().numpy(), G.astype(np.float64), N)) <= TOL

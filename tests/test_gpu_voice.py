@@ -153,6 +153,28 @@ def test_normalize_if_clipping(config1, cuda_device):
                  .abs().max()) <= 1e-6
 
 
+def test_peak_ignores_samples_past_the_clip_end(cuda_device):
+    """T % TILE != 0 (1 s: 44100 = 21 tiles of 2048 + 1092): the threads of the last tile that lie past the end of the
+    clip keep rendering (constant gain of the last control point, running phase) and must not reach max|mixed|.
+    Voices still in their attack at the clip end have their largest gain exactly there, so a phantom sample would
+    beat every real one: peak must equal max|raw| bit for bit."""
+    import ias_b200
+
+    B = 64
+    cfg = ias_b200.SynthConfig(batch_size=B, reproducible=True, sample_rate=44100, buffer_size_seconds=1.0)
+    voice = ias_b200.Voice(synthconfig=cfg, normalize=False).to(cuda_device)
+    voice.randomize(seed=11)
+    one = torch.ones(B, device=cuda_device)
+    voice.keyboard.set_parameter_0to1("duration", one)                       # note held for 4 s
+    for m in ("adsr_1", "adsr_2", "lfo_1_amp_adsr", "lfo_2_amp_adsr"):
+        getattr(voice, m).set_parameter_0to1("attack", one)                  # 2 s attack: still rising at 1 s
+        getattr(voice, m).set_parameter_0to1("sustain", one)
+    raw, peak = voice.output(return_peak=True)
+    assert raw.shape == (B, 44100) and 44100 % 2048 != 0
+    assert torch.equal(peak, raw.abs().max(dim=1)[0])
+    assert float(peak.max()) > 0.0
+
+
 def test_non_reproducible_noise_and_odd_lengths(cuda_device):
     """reproducible=False: noise is [B,T] (vicreg_audio_params.py:86-91 uses this); T % 8 != 0 takes the scalar path."""
     B = 32

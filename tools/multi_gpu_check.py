@@ -1,7 +1,8 @@
 """torchrun --nproc-per-node W tools/multi_gpu_check.py : N-rank loss == oracle on the rank-ordered concatenation.
 
-Checks the embedding all-gather on real GPUs through both routes (torch.distributed NCCL and the C-ABI
-communicator in libias_comm.so), plus the sharded front end: rank r renders sound ids [(step*W + r)*B_local, ...).
+Checks the embedding exchange on real GPUs through every route (torch.distributed NCCL, the C-ABI
+communicator in libias_comm.so, the fused peer-read gather and the statistics exchange), forward and backward, plus
+the sharded front end: rank r renders sound ids [(step*W + r)*B_local, ...).
 Rank 0 prints PASS/FAIL lines and exits non-zero on failure."""
 import os
 import sys
@@ -74,6 +75,33 @@ def main():
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         if rank == 0:
             print(f"{'PASS' if flags.item() else 'FAIL'} fused gather round {it}: rel {rel} grad rel {egx:.2e} {egy:.2e}")
+        ok = ok and bool(flags.item())
+    ias_b200.use_fused_gather(None)
+    # statistics exchange (default route of bench.py): every rank reduces its own rows, pushes a summary to its peers
+    # from inside the loss kernels and combines the W summaries with the pooled formulas
+    sx = ias_b200.StatsExchange(D, dev)
+    ias_b200.use_fused_gather(sx)
+    for it in range(4):  # several rounds: both parities of the double-buffered inbox, twice
+        xs = (x_all[sl] * (1.0 + 0.25 * it) + 0.3 * rank).to(dev).requires_grad_(True)   # rank-dependent means
+        ys = (y_all[sl] - 0.5 * it).to(dev).requires_grad_(True)
+        out = ias_b200.vicreg_loss(xs, ys, world * B_local, D, 25.0, 25.0, 1.0)
+        if it == 2:  # a second (diagnostic) forward before the backward of the first must not disturb it
+            with torch.no_grad():
+                ias_b200.vicreg_loss(ys.detach() * 2.0, xs.detach(), world * B_local, D, 25.0, 25.0, 1.0)
+        out[0].backward()
+        shift = torch.arange(world, dtype=torch.float32).repeat_interleave(B_local)[:, None] * 0.3
+        xa, ya = (x_all * (1.0 + 0.25 * it) + shift).numpy(), (y_all - 0.5 * it).numpy()
+        want_it = np.array(OV.loss(xa, ya, world * B_local, D, local_rows=sl))
+        got = np.array([float(o) for o in out])
+        gx_full, gy_full = OV.loss_grad(xa, ya, world * B_local, D)
+        egx = np.abs(xs.grad.cpu().numpy() - world * gx_full[sl]).max() / np.abs(world * gx_full[sl]).max()
+        egy = np.abs(ys.grad.cpu().numpy() - world * gy_full[sl]).max() / np.abs(world * gy_full[sl]).max()
+        rel = np.abs(got - want_it) / np.abs(want_it)
+        good = bool(np.all(rel <= 1e-4)) and egx <= 1e-4 and egy <= 1e-4
+        flags = torch.tensor([1 if good else 0], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"{'PASS' if flags.item() else 'FAIL'} statistics exchange round {it}: rel {rel} grad rel {egx:.2e} {egy:.2e}")
         ok = ok and bool(flags.item())
     ias_b200.use_fused_gather(None)
     # sharded front end: this rank's sounds equal the same ids rendered by a single process
