@@ -217,6 +217,16 @@ IAS_API size_t ias_vicreg_stats_buffer_bytes(int world, int D);
 IAS_API int ias_vicreg_loss_stats(const float* x, const float* y, float* const* buffers_host, int world, int rank,
                           int B_local, int cfg_batch_size, int D, int embeddim, float sim_coeff, float std_coeff,
                           float cov_coeff, float* out4, void* workspace, size_t workspace_bytes, ias_stream_t stream);
+/* The same call split at the exchange, so a caller can put other work between sending its summary and needing the
+ * peers': IAS_STATS_STAGE_PUBLISH runs the local reduction and pushes the summary (out4 unused);
+ * IAS_STATS_STAGE_COMBINE waits for every rank's summary of this step, combines and writes out4.  Both bits =
+ * ias_vicreg_loss_stats.  (tools/stats_emulate.py uses the split to run W emulated ranks on one GPU in two sweeps.) */
+#define IAS_STATS_STAGE_PUBLISH 1
+#define IAS_STATS_STAGE_COMBINE 2
+IAS_API int ias_vicreg_loss_stats_stages(const float* x, const float* y, float* const* buffers_host, int world, int rank,
+                                 int B_local, int cfg_batch_size, int D, int embeddim, float sim_coeff,
+                                 float std_coeff, float cov_coeff, float* out4, void* workspace,
+                                 size_t workspace_bytes, int stages, ias_stream_t stream);
 /* Gradient w.r.t. this rank's rows summed over all ranks' losses (FullGatherLayer.backward, vicreg.py:92-95): the
  * std/cov terms are identical on every rank, so it is `world` times the own-row slice -- no communication.  Same
  * x, y and workspace as the preceding ias_vicreg_loss_stats. */

@@ -1269,6 +1269,17 @@ extern "C" int ias_vicreg_loss_stats(const float* x, const float* y, float* cons
                                      int B_local, int cfg_batch_size, int D, int embeddim, float sim_coeff,
                                      float std_coeff, float cov_coeff, float* out4, void* workspace,
                                      size_t workspace_bytes, ias_stream_t stream) {
+  return ias_vicreg_loss_stats_stages(x, y, buffers_host, world, rank, B_local, cfg_batch_size, D, embeddim, sim_coeff,
+                                      std_coeff, cov_coeff, out4, workspace, workspace_bytes,
+                                      IAS_STATS_STAGE_PUBLISH | IAS_STATS_STAGE_COMBINE, stream);
+}
+
+extern "C" int ias_vicreg_loss_stats_stages(const float* x, const float* y, float* const* buffers_host, int world,
+                                            int rank, int B_local, int cfg_batch_size, int D, int embeddim,
+                                            float sim_coeff, float std_coeff, float cov_coeff, float* out4,
+                                            void* workspace, size_t workspace_bytes, int stages, ias_stream_t stream) {
+  const bool do_publish = (stages & IAS_STATS_STAGE_PUBLISH) != 0, do_combine = (stages & IAS_STATS_STAGE_COMBINE) != 0;
+  IAS_REQUIRE(do_publish || do_combine, IAS_ERR_INVALID, "ias_vicreg_loss_stats: stages=%d selects nothing", stages);
   int rc = check_common(x, B_local, D, workspace, workspace_bytes, "ias_vicreg_loss_stats");
   if (rc) return rc;
   IAS_REQUIRE(y && out4 && buffers_host, IAS_ERR_INVALID, "ias_vicreg_loss_stats: NULL pointer");
@@ -1287,7 +1298,7 @@ extern "C" int ias_vicreg_loss_stats(const float* x, const float* y, float* cons
   float* w = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);
   // local rows -> local mean, centred second moments, K-split Gram partials (the single-GPU kernels, B = B_local)
-  {
+  if (do_publish) {
     bool v4 = (p.D % 4 == 0) && ias_aligned16(x) && ias_aligned16(y);
     ProfScope prof_(K_VICREG_COLSUM, st);
     if (v4)
@@ -1298,22 +1309,25 @@ extern "C" int ias_vicreg_loss_stats(const float* x, const float* y, float* cons
                                     nullptr, nullptr);
   }
   IAS_LAUNCH_CHECK("k_colsum");
-  {
+  if (do_publish) {
     ProfScope prof_(K_VICREG_PACK, st);
     k_center_pack<<<dim3(p.NV, 2), 256, 0, st>>>(x, y, p.B, p.D, p.P, p.DT, p.KB, w + p.off_partial, w + p.off_mean,
                                                 w + p.off_varpart, w + p.off_packed);
   }
   IAS_LAUNCH_CHECK("k_center_pack");
-  rc = launch_gram(p, w, st);
-  if (rc) return rc;
+  if (do_publish) {
+    rc = launch_gram(p, w, st);
+    if (rc) return rc;
+  }
   const size_t pf = packet_floats(p.Dp, p.ntiles);
-  {
+  if (do_publish) {
     ProfScope prof_(K_VICREG_STATS_PUBLISH, st);
     const int grid = (int)((pf / 4 + 255) / 256);
     k_stats_publish<<<grid, 256, 0, st>>>(w + p.off_gram, w + p.off_varpart, w + p.off_mean, D, p.Dp, p.ntiles, p.splits,
                                           p.NV, peers, world, rank);
   }
   IAS_LAUNCH_CHECK("k_stats_publish");
+  if (!do_combine) return IAS_OK;
   {
     // the combine overwrites the local mean with the global one and leaves the global centred second moments where
     // k_finalize reads variance partials (as a single partial)

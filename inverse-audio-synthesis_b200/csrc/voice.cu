@@ -528,7 +528,7 @@ __device__ __forceinline__ P2 vco_increment_p2(float midi, float depth, P2 mod, 
 }
 
 // vm::reduce_half_turns for two arguments: a = (n + f) * pi, f in [-0.5, 0.5]; t carries n in its low mantissa bits.
-__device__ __forceinline__ void reduce_half_turns_p2(P2 a, P2& f, P2& t) {
+[[maybe_unused]] __device__ __forceinline__ void reduce_half_turns_p2(P2 a, P2& f, P2& t) {
   const float C1 = 0.318309873342514038f;
   const float C2 = (float)(0.31830988618379067154 - (double)0.318309873342514038f);
   const float magic = 12582912.0f;
@@ -536,22 +536,78 @@ __device__ __forceinline__ void reduce_half_turns_p2(P2 a, P2& f, P2& t) {
   const P2 nneg = p2_sub(p2b(magic), t);  // -rint(a / pi)
   f = p2_fma(a, p2b(C2), p2_fma(a, p2b(C1), nneg));
 }
-// cos(a) for the sine VCO: reduce to full turns, f in [-0.5, 0.5] (same FMA scheme as reduce_half_turns with 1/(2 pi)),
-// so the SFU cosine needs no sign fix-up afterwards.  Amplitude path: absolute error ~5e-7.
+// Oscillator arguments are reduced in RADIANS with a two-constant Cody-Waite step: n = rint(a / P) from one FMA against
+// the 1.5 * 2^23 magic constant, then y = fma(-n, P_hi, a) (exact product, ONE rounding relative to the small result,
+// so accuracy near the zeros of sin is kept) and y = fma(-n, P_lo, y) (P_lo = P - P_hi, |n P_lo| <= 0.07 for 30 s
+// clips, its own error <= 5e-9).  The SFU cosine then takes y as it is -- reducing to turns costs one more multiply by
+// 2 pi that cos.approx undoes again (FMUL.RZ by 1/(2 pi) + MUFU.COS).  Amplitude path: absolute error ~5e-7.
+#ifndef IAS_AUDIO_RADIANS
+#define IAS_AUDIO_RADIANS 1
+#endif
+// cos(a) for the sine VCO: P = 2 pi, y in [-pi, pi].
 __device__ __forceinline__ P2 cos_arg_p2(P2 a) {
+  const float magic = 12582912.0f;
+#if IAS_AUDIO_RADIANS
+  const float C1 = 0.159154936671257019f;                        // (float)(1/(2 pi))
+  const float P_HI = 6.2831854820251465f, P_LO = -1.7484555314695172e-07f;
+  const P2 t = p2_fma(a, p2b(C1), p2b(magic));
+  const P2 nneg = p2_sub(p2b(magic), t);                          // -rint(a / (2 pi)), exact
+  const P2 y = p2_fma(nneg, p2b(P_LO), p2_fma(nneg, p2b(P_HI), a));
+  return p2(__cosf(p2lo(y)), __cosf(p2hi(y)));
+#else
   const float C1 = 0.159154936671257019f;                                              // (float)(1/(2 pi))
   const float C2 = (float)(0.15915494309189533577 - (double)0.159154936671257019f);    // 1/(2 pi) - C1
-  const float magic = 12582912.0f;
   const P2 t = p2_fma(a, p2b(C1), p2b(magic));
   const P2 nneg = p2_sub(p2b(magic), t);
   const P2 fr = p2_mul(p2_fma(a, p2b(C2), p2_fma(a, p2b(C1), nneg)), p2b(IAS_TWO_PI_F));
   return p2(__cosf(p2lo(fr)), __cosf(p2hi(fr)));
+#endif
 }
-// vm::squaresaw_core for two arguments: tanh(pk * sin(a)) * (1 + shape * cos(a)).  With a = (n + f) * pi and
-// sigma = (-1)^n: sin(a) = sigma * sin(pi f), cos(a) = sigma * cos(pi f), and tanh is odd, so the product equals
-// tanh(pk * sin(pi f)) * (sigma + shape * cos(pi f)) -- the parity enters once, as the float +-1 (one shift-add).
+// vm::squaresaw_core for two arguments: tanh(pk * sin(a)) * (1 + shape * cos(a)).  With a = n pi + y and
+// sigma = (-1)^n: sin(a) = sigma * sin(y), cos(a) = sigma * cos(y), and tanh is odd, so the product equals
+// tanh(pk * sin(y)) * (sigma + shape * cos(y)) -- the parity enters once, as the float +-1 (one shift-add).
 __device__ __forceinline__ float parity_sign(float t) { return i2f((f2i(t) << 31) + 0x3f800000); }
-__device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
+#ifndef IAS_AUDIO_PKFOLD
+#define IAS_AUDIO_PKFOLD 0
+#endif
+struct SinCoef {  // pk * Q's coefficients (per voice) when IAS_AUDIO_PKFOLD, else unused
+  float c[5];
+};
+__device__ __forceinline__ SinCoef sin_coef(float pk) {
+  SinCoef q;
+  q.c[0] = pk * 9.9999994040e-01f; q.c[1] = pk * -1.6666640341e-01f; q.c[2] = pk * 8.3326986060e-03f;
+  q.c[3] = pk * -1.9786701887e-04f; q.c[4] = pk * 2.5610734156e-06f;
+  return q;
+}
+__device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape, const SinCoef& sq) {
+#if IAS_AUDIO_RADIANS
+  // P = pi, y in [-pi/2, pi/2] (may overshoot by an ulp of a/pi); sin(y) = y * Q(y^2), the degree-9 polynomial of
+  // vm::sinpi_poly rescaled to radians (relative error <= 2.5e-7 on |y| <= 1.77: the zero crossings SquareSawVCO
+  // amplifies through tanh stay accurate)
+  const float magic = 12582912.0f;
+  const float C1 = 0.318309873342514038f;                        // (float)(1/pi)
+  const float P_HI = 3.1415927410125732f, P_LO = -8.7422776573475858e-08f;
+  const P2 t = p2_fma(a, p2b(C1), p2b(magic));
+  const P2 nneg = p2_sub(p2b(magic), t);
+  const P2 y = p2_fma(nneg, p2b(P_LO), p2_fma(nneg, p2b(P_HI), a));
+  const P2 u = p2_mul(y, y);
+#if IAS_AUDIO_PKFOLD
+  P2 p = p2b(sq.c[4]);  // pk folded into the (per-voice) coefficients: one multiply less per sample pair
+  p = p2_fma(p, u, p2b(sq.c[3]));
+  p = p2_fma(p, u, p2b(sq.c[2]));
+  p = p2_fma(p, u, p2b(sq.c[1]));
+  p = p2_fma(p, u, p2b(sq.c[0]));
+  const P2 sc = p2_mul(p, y);  // pk * sin(y)
+#else
+  P2 p = p2b(2.5610734156e-06f);
+  p = p2_fma(p, u, p2b(-1.9786701887e-04f));
+  p = p2_fma(p, u, p2b(8.3326986060e-03f));
+  p = p2_fma(p, u, p2b(-1.6666640341e-01f));
+  p = p2_fma(p, u, p2b(9.9999994040e-01f));
+  const P2 sc = p2_mul(p2b(pk), p2_mul(p, y));  // pk * sin(y)
+#endif
+  const P2 fr = y;
+#else
   P2 f, t;
   reduce_half_turns_p2(a, f, t);
   const P2 u = p2_mul(f, f);
@@ -561,6 +617,8 @@ __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
   p = p2_fma(p, u, p2b(-5.1677045822143555f));
   p = p2_fma(p, u, p2b(3.141592502593994f));
   const P2 sc = p2_mul(p2b(pk), p2_mul(p, f));  // pk * sin(pi f)
+  const P2 fr = p2_mul(f, p2b(IAS_PI_F));
+#endif
   float e0, e1, r0, r1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(p2lo(sc)));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(p2hi(sc)));
@@ -568,7 +626,6 @@ __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p2lo(ep)));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p2hi(ep)));
   const P2 th = p2_fma(p2b(-2.0f), p2(r0, r1), p2b(1.0f));
-  const P2 fr = p2_mul(f, p2b(IAS_PI_F));
   const P2 c = p2(__cosf(p2lo(fr)), __cosf(p2hi(fr)));
   return p2_mul(th, p2_fma(p2b(shape), c, p2(parity_sign(p2lo(t)), parity_sign(p2hi(t)))));
 }
@@ -633,6 +690,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
     const float midi1 = vc[VC_MIDI1], depth1 = vc[VC_DEPTH1], phase1 = vc[VC_PHASE1];
     const float midi2 = vc[VC_MIDI2], depth2 = vc[VC_DEPTH2], phase2 = vc[VC_PHASE2];
     const float pk = vc[VC_PK], shape = vc[VC_SHAPE];
+    const SinCoef sq = sin_coef(pk);
     const bool noclamp = vc[VC_NOCLAMP] != 0.0f;
     const float4* rec = A.rec + (size_t)b * C * (REC_FLOATS / 4);
     const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
@@ -734,7 +792,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
         const P2 g2 = p2_fma(r, p2b(r2.w), p2_fma(u, p2b(r2.z), p2b(r2.y)));
         const P2 g3 = p2_fma(r, p2b(r3.z), p2_fma(u, p2b(r3.y), p2b(r3.x)));
         const P2 yy = p2_fma(cos_arg_p2(arg1), g1,
-                             p2_fma(squaresaw_core_p2(arg2, pk, shape), g2, p2_mul(p2(nzv[k], nzv[k + 1]), g3)));
+                             p2_fma(squaresaw_core_p2(arg2, pk, shape, sq), g2, p2_mul(p2(nzv[k], nzv[k + 1]), g3)));
         y[k] = p2lo(yy);
         y[k + 1] = p2hi(yy);
         if (VEC || (t0 + k) < T) lpeak = fmaxf(lpeak, fabsf(y[k]));

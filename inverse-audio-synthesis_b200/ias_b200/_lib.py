@@ -106,6 +106,11 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p,
          c_void_p, c_size_t, c_void_p],
     ),
+    "ias_vicreg_loss_stats_stages": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p,
+         c_void_p, c_size_t, c_int, c_void_p],
+    ),
     "ias_vicreg_loss_stats_backward": (
         c_int,
         [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,

@@ -42,7 +42,7 @@ def test_front_end_step_vs_oracle(cuda_device):
     band_err = float((bands.cpu() - ref["bands"]).abs().max() / ref["bands"].abs().max())
     print("bands rel err", band_err, "embedding rel err",
           float((x.cpu() - ref["x"]).abs().max() / ref["x"].abs().max()))
-    assert np.all(rel <= 1e-3)
+    assert np.all(rel <= 2e-5)  # measured 1e-6 (loss terms average the few ill-conditioned voices away); bound 1e-4
     # loss on the ORACLE embeddings isolates the loss kernels: north-star tolerance
     with torch.no_grad():
         out2 = vic.loss(ref["x"].to(cuda_device), ref["y"].to(cuda_device))

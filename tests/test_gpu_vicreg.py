@@ -155,6 +155,48 @@ def test_backward_of_individual_terms_and_local_rows(cuda_device):
     assert float((gyd.cpu() + want).abs().max()) <= 1e-6 * float(want.abs().max())
 
 
+def test_two_forwards_before_the_first_backward_keep_their_own_state(cuda_device):
+    """A second VICReg.loss() on the same module before the first backward (two view pairs, a diagnostic loss on another
+    batch, a different B) must not disturb the first one's gradients: the C ABI keeps the backward's inputs in the
+    workspace of the forward call, so every differentiable forward owns its workspace (ias_b200/vicreg.py)."""
+    import ias_b200
+
+    D = 256
+    m = ias_b200.VICReg(_cfg(D, D, 512), torch.nn.Identity(), torch.nn.Identity())
+
+    def grads(x, y, between=None):
+        xd = x.to(cuda_device).requires_grad_(True)
+        yd = y.to(cuda_device).requires_grad_(True)
+        out = m.loss(xd, yd)
+        if between is not None:
+            between()
+        out[0].backward()
+        return xd.grad.clone(), yd.grad.clone(), torch.stack([o.detach() for o in out])
+
+    x1, y1 = MG.vicreg_inputs(512, D, "correlated", seed=5)
+    x2, y2 = MG.vicreg_inputs(384, D, "correlated", seed=6)
+    want = grads(x1, y1)
+    held = []
+
+    def other_grad_forward():  # differentiable forward on another batch and another B, left pending
+        a = (x2 * 3.0).to(cuda_device).requires_grad_(True)
+        held.append((a, m.loss(a, y2.to(cuda_device))))
+
+    def other_nograd_forward():
+        with torch.no_grad():
+            m.loss((y1 * 2.0).to(cuda_device), x1.to(cuda_device))
+
+    for between in (other_grad_forward, other_nograd_forward):
+        got = grads(x1, y1, between)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    # the pending forward still back-propagates its own state afterwards
+    a, out = held[0]
+    out[0].backward()
+    gx, _ = OV.loss_grad((x2 * 3.0).numpy(), y2.numpy(), 512, D)
+    assert np.abs(a.grad.cpu().numpy() - gx).max() <= 1e-4 * np.abs(gx).max()
+
+
 def test_bad_arguments_fail_loudly(cuda_device):
     from ias_b200 import _lib
     import ias_b200

@@ -137,3 +137,19 @@ def test_voice_oracle_shapes_and_ranges():
     assert bool(is_train.all())  # ids 224..255 -> (id//32)%10 == 7
     assert not bool(V.is_train(9, 32).any())  # ids 288..319 -> block 9 is the held-out one
     assert (params >= 0).all() and (params < 1).all()
+
+
+def test_voice_oracle_has_not_drifted():
+    """oracle/voice.py against the committed fixture of its own output (oracle/make_voice_fixture.py): the Voice oracle
+    is unpinned w.r.t. torchsynth, but it cannot change silently."""
+    from oracle import make_voice_fixture as F
+
+    want = np.load(os.path.join(GOLDEN, "voice_oracle.npz"))
+    got = F.compute()
+    assert list(got["params_sha"]) == list(want["params_sha"])      # MT19937 + 24-bit mantissa: host independent
+    assert list(got["noise_sha"]) == list(want["noise_sha"])
+    assert np.array_equal(got["is_train"], want["is_train"])
+    assert np.abs(got["adsr"] - want["adsr"]).max() <= 2e-7
+    assert np.abs(got["ctrl"] - want["ctrl"]).max() <= 5e-7
+    err = np.abs(got["audio"] - want["audio"]).max(axis=1)
+    assert np.median(err) <= 1e-5 and np.abs(got["peak"] - want["peak"]).max() <= 1e-3

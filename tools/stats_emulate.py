@@ -1,8 +1,8 @@
 """python tools/stats_emulate.py [W] -- the statistics exchange (ias_vicreg_loss_stats) with W emulated ranks on ONE GPU.
 
 Every emulated rank has its own exchange buffer (plain device memory: peer-accessible by construction), workspace and
-CUDA stream; the W calls are enqueued back to back and run concurrently, so each rank's combine kernel really waits on
-flags the other ranks' publish kernels raise.  Checks, for several steps (both inbox parities) and rank-dependent means:
+CUDA stream; all ranks publish, then all ranks combine (ias_vicreg_loss_stats_stages), so each rank's combine kernel
+reads the summaries and flags the other ranks' publish kernels wrote into its inbox.  Checks, for several steps (both inbox parities) and rank-dependent means:
 every rank's four loss terms == oracle on the rank-ordered concatenation (<= 1e-4 relative), std/cov terms
 bit-identical across ranks, backward == world x the single-process gradient on the own rows (vicreg.py:92-95).
 Runs in its own process (tests/test_gpu_multi.py) so that a timeout trap cannot poison the caller's CUDA context."""
@@ -48,12 +48,18 @@ def main():
         xs = [xa[q * B_local:(q + 1) * B_local].contiguous().to(dev) for q in range(W)]
         ys = [ya[q * B_local:(q + 1) * B_local].contiguous().to(dev) for q in range(W)]
         torch.cuda.synchronize()
-        for q in range(W):
-            with torch.cuda.stream(streams[q]):
-                rc = lib.ias_vicreg_loss_stats(_lib.ptr(xs[q]), _lib.ptr(ys[q]), ptrs, W, q, B_local, W * B_local, D, D,
-                                               25.0, 25.0, 1.0, _lib.ptr(outs[q]), _lib.ptr(wss[q]),
-                                               wss[q].numel() * 4, ctypes.c_void_p(streams[q].cuda_stream))
-                _lib.check(rc, "ias_vicreg_loss_stats")
+        # two sweeps (publish on every rank, then combine on every rank): ranks that share a GPU cannot be relied on to
+        # run concurrently -- a combine kernel spinning on every SM keeps the tcgen05 Gram kernel of a later rank (which
+        # needs the SMs re-partitioned for 197 KB of shared memory) from starting.  Across real GPUs the single call is
+        # used (tools/multi_gpu_check.py).  Each rank still runs on its own stream, so the sweeps interleave freely.
+        for stage in (1, 2):
+            for q in range(W):
+                with torch.cuda.stream(streams[q]):
+                    rc = lib.ias_vicreg_loss_stats_stages(
+                        _lib.ptr(xs[q]), _lib.ptr(ys[q]), ptrs, W, q, B_local, W * B_local, D, D, 25.0, 25.0, 1.0,
+                        _lib.ptr(outs[q]), _lib.ptr(wss[q]), wss[q].numel() * 4, stage,
+                        ctypes.c_void_p(streams[q].cuda_stream))
+                    _lib.check(rc, "ias_vicreg_loss_stats_stages")
         torch.cuda.synchronize()
         got = np.stack([o.cpu().numpy() for o in outs])
         gx_full, gy_full = OV.loss_grad(xa.numpy(), ya.numpy(), W * B_local, D)
