@@ -42,9 +42,13 @@ def parse():
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e leg: eager launches instead of a CUDA graph replay")
-    ap.add_argument("--pipeline", action="store_true",
-                    help="overlap the next batch's control stage (Voice.prepare, side stream) with this batch's PQMF / "
-                         "loss; measured +2.3 %% (1.250 -> 1.222 ms/step), off by default so a step is self-contained")
+    ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
+                    help="by default a step renders the batch whose control stage the previous step prepared and, on a "
+                         "side stream under this batch's PQMF / exchange / loss, seeds and prepares the next batch "
+                         "(Voice.prepare: seed -> ADSR -> control -> schedule; same kernels, bit-identical results, "
+                         "tests/test_gpu_e2e.py); --no-pipeline runs every stage of a batch back to back "
+                         "(measured on B200: 1.249 vs 1.223 ms/step)")
+    ap.set_defaults(pipeline=True)
     ap.add_argument("--gather", default="stats", choices=["stats", "peer", "nccl"],
                     help="N>1 embedding exchange: stats = every rank reduces its own rows and pushes a 0.4 MB summary "
                          "(mean, second moments, Gram) to its peers over NVLink from inside the loss kernels; peer = the "

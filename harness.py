@@ -82,7 +82,8 @@ def oracle_front_end(batch_idx: int, B: int, N: int = 3, seconds: float = 4.0, c
     from oracle import vicreg as OV
     from oracle import voice as OVc
 
-    cfg = OVc.SynthConfigO(batch_size=B, buffer_size_seconds=seconds, reproducible=reproducible)
+    # (a partial batch of a reproducible render -- B % 32 != 0 -- still uses the 32-row noise table, row b % 32)
+    cfg = OVc.SynthConfigO(batch_size=B, buffer_size_seconds=seconds, reproducible=reproducible and B % 32 == 0)
     t0 = time.perf_counter()
     u = OVc.seeded_params(batch_idx, B)
     t1 = time.perf_counter()

@@ -567,19 +567,7 @@ __device__ __forceinline__ P2 cos_arg_p2(P2 a) {
 // sigma = (-1)^n: sin(a) = sigma * sin(y), cos(a) = sigma * cos(y), and tanh is odd, so the product equals
 // tanh(pk * sin(y)) * (sigma + shape * cos(y)) -- the parity enters once, as the float +-1 (one shift-add).
 __device__ __forceinline__ float parity_sign(float t) { return i2f((f2i(t) << 31) + 0x3f800000); }
-#ifndef IAS_AUDIO_PKFOLD
-#define IAS_AUDIO_PKFOLD 0
-#endif
-struct SinCoef {  // pk * Q's coefficients (per voice) when IAS_AUDIO_PKFOLD, else unused
-  float c[5];
-};
-__device__ __forceinline__ SinCoef sin_coef(float pk) {
-  SinCoef q;
-  q.c[0] = pk * 9.9999994040e-01f; q.c[1] = pk * -1.6666640341e-01f; q.c[2] = pk * 8.3326986060e-03f;
-  q.c[3] = pk * -1.9786701887e-04f; q.c[4] = pk * 2.5610734156e-06f;
-  return q;
-}
-__device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape, const SinCoef& sq) {
+__device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
 #if IAS_AUDIO_RADIANS
   // P = pi, y in [-pi/2, pi/2] (may overshoot by an ulp of a/pi); sin(y) = y * Q(y^2), the degree-9 polynomial of
   // vm::sinpi_poly rescaled to radians (relative error <= 2.5e-7 on |y| <= 1.77: the zero crossings SquareSawVCO
@@ -591,21 +579,14 @@ __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape, con
   const P2 nneg = p2_sub(p2b(magic), t);
   const P2 y = p2_fma(nneg, p2b(P_LO), p2_fma(nneg, p2b(P_HI), a));
   const P2 u = p2_mul(y, y);
-#if IAS_AUDIO_PKFOLD
-  P2 p = p2b(sq.c[4]);  // pk folded into the (per-voice) coefficients: one multiply less per sample pair
-  p = p2_fma(p, u, p2b(sq.c[3]));
-  p = p2_fma(p, u, p2b(sq.c[2]));
-  p = p2_fma(p, u, p2b(sq.c[1]));
-  p = p2_fma(p, u, p2b(sq.c[0]));
-  const P2 sc = p2_mul(p, y);  // pk * sin(y)
-#else
+  // (folding pk into per-voice coefficients saves this multiply but costs five registers: measured slower, 0.725 vs
+  // 0.719 ms, more spills)
   P2 p = p2b(2.5610734156e-06f);
   p = p2_fma(p, u, p2b(-1.9786701887e-04f));
   p = p2_fma(p, u, p2b(8.3326986060e-03f));
   p = p2_fma(p, u, p2b(-1.6666640341e-01f));
   p = p2_fma(p, u, p2b(9.9999994040e-01f));
   const P2 sc = p2_mul(p2b(pk), p2_mul(p, y));  // pk * sin(y)
-#endif
   const P2 fr = y;
 #else
   P2 f, t;
@@ -690,7 +671,6 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
     const float midi1 = vc[VC_MIDI1], depth1 = vc[VC_DEPTH1], phase1 = vc[VC_PHASE1];
     const float midi2 = vc[VC_MIDI2], depth2 = vc[VC_DEPTH2], phase2 = vc[VC_PHASE2];
     const float pk = vc[VC_PK], shape = vc[VC_SHAPE];
-    const SinCoef sq = sin_coef(pk);
     const bool noclamp = vc[VC_NOCLAMP] != 0.0f;
     const float4* rec = A.rec + (size_t)b * C * (REC_FLOATS / 4);
     const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
@@ -792,7 +772,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
         const P2 g2 = p2_fma(r, p2b(r2.w), p2_fma(u, p2b(r2.z), p2b(r2.y)));
         const P2 g3 = p2_fma(r, p2b(r3.z), p2_fma(u, p2b(r3.y), p2b(r3.x)));
         const P2 yy = p2_fma(cos_arg_p2(arg1), g1,
-                             p2_fma(squaresaw_core_p2(arg2, pk, shape, sq), g2, p2_mul(p2(nzv[k], nzv[k + 1]), g3)));
+                             p2_fma(squaresaw_core_p2(arg2, pk, shape), g2, p2_mul(p2(nzv[k], nzv[k + 1]), g3)));
         y[k] = p2lo(yy);
         y[k + 1] = p2hi(yy);
         if (VEC || (t0 + k) < T) lpeak = fmaxf(lpeak, fabsf(y[k]));

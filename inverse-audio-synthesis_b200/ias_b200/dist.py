@@ -179,7 +179,7 @@ class FusedGatherLoss(torch.autograd.Function):
             raise _lib.IasError(f"EmbeddingExchange was built for [{ex.b_local},{ex.D}], got {tuple(x.shape)}")
         ex.publish(x.float(), y.float())
         # a forward that may be differentiated owns its workspace (see vicreg._VicregLossFn)
-        grad = needs_backward(x, y)
+        grad = needs_backward(ctx)
         ws = aligned_workspace(_lib.lib().ias_vicreg_gather_workspace_bytes(ex.world, ex.b_local, ex.D),
                                x.device) if grad else ex.ws()
         out4 = torch.empty(4, dtype=torch.float32, device=x.device)
@@ -223,7 +223,7 @@ class FusedStatsLoss(torch.autograd.Function):
         yc = y.detach().to(torch.float32).contiguous()
         b_local = xc.shape[0]
         lib = _lib.lib()
-        grad = needs_backward(x, y)
+        grad = needs_backward(ctx)
         ws = aligned_workspace(lib.ias_vicreg_workspace_bytes(b_local, ex.D), xc.device) if grad else ex.ws(b_local)
         out4 = torch.empty(4, dtype=torch.float32, device=xc.device)
         with _lib.on_device(xc):

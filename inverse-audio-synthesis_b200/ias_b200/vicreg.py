@@ -94,8 +94,9 @@ def aligned_workspace(nbytes: int, device) -> torch.Tensor:
     return raw[shift:shift + nbytes // 4]
 
 
-def needs_backward(*tensors) -> bool:
-    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+def needs_backward(ctx) -> bool:
+    """Inside ``autograd.Function.forward`` (where grad mode is off): will autograd call ``backward`` for x or y?"""
+    return bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
 
 
 class _VicregLossFn(torch.autograd.Function):
@@ -113,7 +114,7 @@ class _VicregLossFn(torch.autograd.Function):
         yc = y.detach().to(torch.float32).contiguous()
         B, D = xc.shape
         lib = _lib.lib()
-        if needs_backward(x, y):
+        if needs_backward(ctx):
             ws = aligned_workspace(lib.ias_vicreg_workspace_bytes(B, D), xc.device)
         else:
             ws = holder.workspace(B, D, xc.device)
