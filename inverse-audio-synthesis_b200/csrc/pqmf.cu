@@ -250,7 +250,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   constexpr int SPAN4 = (SPAN + 3) / 4;
   __shared__ __align__(16) float xs[Pad<S>::floats(SPAN4 * 4)];
   __shared__ int s_bound[POOL ? N : 1][2];                        // per band: start of bin ilo+1, end of bin ilo
-  __shared__ __align__(16) float s_pool[POOL ? N : 1][POOL ? TILE_N : 4];  // the tile's band values, one row per band
+  __shared__ __align__(16) float s_pool[POOL ? N : 1][POOL ? PQ_THREADS : 4];  // per-thread sums of |v|, one row per band
+  __shared__ float s_mix[POOL ? N : 1][PQ_THREADS / 32][2];                    // bin-slot sums of boundary warps
 
   const int b = blockIdx.x / tiles_per_row;
   const int tile = blockIdx.x - b * tiles_per_row;
@@ -415,13 +416,7 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   }
 
   if constexpr (POOL) {
-    // Phase 1 (every thread): park the band values in shared memory, Q consecutive steps per thread and band -- 128-bit
-    // stores, no arithmetic.  Phase 2 (warp r % NW for band r): a lane adds up |v| of 4Q consecutive steps in a fixed
-    // order and credits the sum to the bin slot its range lies in; only the (at most two) lanes whose range touches
-    // the bin boundary split theirs element by element.  Shuffle tree, lane 0 writes partial[b][r][tile][0..1].
     constexpr int NW = PQ_THREADS / 32;
-    constexpr int PER_LANE = TILE_N / 32;  // 4 Q
-    static_assert(Q % 2 == 0 && PER_LANE % 4 == 0, "pooled epilogue layout");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (n_tile + TILE_N > L) {  // last tile of a row (CTA-uniform, rare): steps past the end contribute nothing
       const int nv = L - n0;
@@ -432,50 +427,69 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
           for (int k = 0; k < N; ++k) acc[q][k] = 0.0f;
         }
     }
+    // Per thread and band one value (the sum of its |v|) goes to shared memory; a warp whose 32*Q elements all lie in
+    // one bin (the usual case: bins are ~5 warps wide) is credited to that bin as a whole after the barrier.  Only a
+    // warp that straddles the bin boundary splits its sum itself (shuffle tree) into s_mix.
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      float* dst = &s_pool[k][threadIdx.x * Q];
-      if constexpr (Q % 4 == 0) {
+      float a[Q];
 #pragma unroll
-        for (int q = 0; q < Q; q += 4)
-          *reinterpret_cast<float4*>(dst + q) = make_float4(acc[q][k], acc[q + 1][k], acc[q + 2][k], acc[q + 3][k]);
-      } else {
+      for (int q = 0; q < Q; ++q) a[q] = fabsf(acc[q][k]);
+      float t = a[0];
 #pragma unroll
-        for (int q = 0; q < Q; q += 2) *reinterpret_cast<float2*>(dst + q) = make_float2(acc[q][k], acc[q + 1][k]);
+      for (int q = 1; q < Q; ++q) t += a[q];
+      s_pool[k][threadIdx.x] = t;
+      const int s1 = s_bound[k][0], e0 = s_bound[k][1];
+      const int wfirst = k * L + n_tile + warp * 32 * Q, wlast = wfirst + 32 * Q - 1;
+      if (!(wlast < s1 || wfirst >= e0)) {  // warp-uniform: this warp straddles the boundary of band k
+        const int f0 = k * L + n0;
+        float sum0 = 0.0f, sum1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          sum0 += (f0 + q < e0) ? a[q] : 0.0f;
+          sum1 += (f0 + q >= s1) ? a[q] : 0.0f;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sum0 += __shfl_xor_sync(0xffffffffu, sum0, o);
+          sum1 += __shfl_xor_sync(0xffffffffu, sum1, o);
+        }
+        if (lane == 0) {
+          s_mix[k][warp][0] = sum0;
+          s_mix[k][warp][1] = sum1;
+        }
       }
     }
     __syncthreads();
+    // band r: lanes 8w..8w+7 hold the 32 per-thread sums of source warp w (4 each); three shuffle steps give the
+    // per-warp sums, which lane 0 credits to the two bin slots in warp order
     for (int r = warp; r < N; r += NW) {
-      float v[PER_LANE];
-#pragma unroll
-      for (int i = 0; i < PER_LANE; i += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(&s_pool[r][lane * PER_LANE + i]);
-        v[i] = fabsf(t.x); v[i + 1] = fabsf(t.y); v[i + 2] = fabsf(t.z); v[i + 3] = fabsf(t.w);
-      }
-      float tot = v[0];
-#pragma unroll
-      for (int i = 1; i < PER_LANE; ++i) tot += v[i];
-      const int s1 = s_bound[r][0], e0 = s_bound[r][1];  // slot 0 = elements < e0, slot 1 = elements >= s1 (s1 <= e0)
-      const int first = r * L + n_tile + lane * PER_LANE;
-      const bool lo = first + PER_LANE - 1 < s1, hi = first >= e0;
-      float c0 = lo ? tot : 0.0f, c1 = hi ? tot : 0.0f;
+      const float4 v = *reinterpret_cast<const float4*>(&s_pool[r][4 * lane]);
+      float t = (v.x + v.y) + (v.z + v.w);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      // every lane resolves the bin slots of its own source warp (lane >> 3) in parallel; lane 0 then adds the NW
+      // contributions in warp order
+      static_assert(NW == 4, "8 lanes per source warp");
+      const int sw = lane >> 3;
+      const int s1 = s_bound[r][0], e0 = s_bound[r][1];
+      const int wfirst = r * L + n_tile + sw * 32 * Q, wlast = wfirst + 32 * Q - 1;
+      const bool lo = wlast < s1, hi = wfirst >= e0;
+      float c0 = lo ? t : 0.0f, c1 = hi ? t : 0.0f;
       if (!lo && !hi) {
-        c0 = 0.0f;
-        c1 = 0.0f;
-#pragma unroll
-        for (int i = 0; i < PER_LANE; ++i) {
-          c0 += (first + i < e0) ? v[i] : 0.0f;
-          c1 += (first + i >= s1) ? v[i] : 0.0f;
-        }
+        c0 = s_mix[r][sw][0];
+        c1 = s_mix[r][sw][1];
       }
+      float slot0 = __shfl_sync(0xffffffffu, c0, 0), slot1 = __shfl_sync(0xffffffffu, c1, 0);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      for (int w = 1; w < NW; ++w) {
+        slot0 += __shfl_sync(0xffffffffu, c0, 8 * w);
+        slot1 += __shfl_sync(0xffffffffu, c1, 8 * w);
       }
       if (lane == 0) {
         float* dst = pool.partial + (((size_t)b * N + r) * tiles_per_row + tile) * 2;
-        *reinterpret_cast<float2*>(dst) = make_float2(c0, c1);
+        *reinterpret_cast<float2*>(dst) = make_float2(slot0, slot1);
       }
     }
   }
@@ -750,7 +764,6 @@ struct SynRows {
   static constexpr int DMIN = Geo::omin();
   static constexpr int HALO = Geo::omax() - DMIN;
   static constexpr int N4 = (N + 3) / 4 * 4;
-  static constexpr int PITCH = 2 * N4;
   // first tap of the block that meets offset o (may be negative / beyond K-1 at the ends)
   __host__ __device__ static constexpr int jb(int o) { return PAD + N * (o - 1) + 1; }
   __host__ __device__ static constexpr int ra() { return ((jb(DMIN) % (2 * N)) + 2 * N) % (2 * N); }
@@ -763,12 +776,18 @@ __global__ void __launch_bounds__(PQ_THREADS)
 k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L, int tiles_per_row,
                        TapsSynSmall<N, K> taps) {
   using R = SynRows<N, K>;
-  constexpr int DMIN = R::DMIN, HALO = R::HALO, N4 = R::N4, PITCH = R::PITCH;
+  constexpr int DMIN = R::DMIN, HALO = R::HALO, N4 = R::N4;
   constexpr int TILE_N = PQ_THREADS * Q;
   constexpr int ROWS = TILE_N + HALO;
   constexpr int PASSES = (ROWS + PQ_THREADS - 1) / PQ_THREADS;
-  static_assert((Q * PITCH / 4) % 2 == 0, "padding scheme assumes an even number of 16-byte units per Q rows");
-  __shared__ __align__(16) float vs[ROWS * PITCH + (ROWS / Q + 1) * 4];
+  // Shared layout: one plane per row half, the half of row r at 16-byte unit r + r/Q of its plane (N4 == 4).  Phase 2
+  // (lane t reads rows Q t + i: units (Q + 1) t + i + i/Q, Q + 1 odd) is free of bank conflicts and its offsets are
+  // compile-time constants; phase 1 (lane = consecutive rows) is conflict free for Q = 8 and has one 2-way pair per
+  // quarter warp for Q = 4.  The interleaved [row][half] layout this replaces had 2-way conflicts on every phase-1
+  // store (ncu: 24.9 M conflicts at N = 3).
+  static_assert(N4 == 4, "plane layout assumes one 16-byte unit per row half");
+  constexpr int UNITS = ROWS + ROWS / Q + 1;
+  __shared__ __align__(16) float vs[2 * UNITS * 4];
 
   const int b = blockIdx.x / tiles_per_row;
   const int tile = blockIdx.x - b * tiles_per_row;
@@ -789,7 +808,7 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
   for (int i = 0; i < PASSES; ++i) {
     const int row = (int)threadIdx.x + i * PQ_THREADS;
     if (row < ROWS) {
-      float* dst = vs + row * PITCH + (row / Q) * 4;
+      float* dst = vs + (row + row / Q) * 4;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float v[N4];
@@ -801,9 +820,7 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
             for (int k = 0; k < N; ++k) v[e] = fmaf(taps.c[k * 2 * N + R::res(h, e)], zk[i][k], v[e]);
           }
         }
-#pragma unroll
-        for (int e = 0; e < N4; e += 4)
-          *reinterpret_cast<float4*>(dst + h * N4 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        *reinterpret_cast<float4*>(dst + h * UNITS * 4) = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
   }
@@ -817,10 +834,10 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
   for (int q = 0; q < Q; ++q)
 #pragma unroll
     for (int p = 0; p < N; ++p) acc[q][p] = 0.0f;
-  const float* base = vs + (int)threadIdx.x * (Q * PITCH + 4);  // row threadIdx.x * Q
+  const float* base = vs + (int)threadIdx.x * (Q + 1) * 4;  // unit of row threadIdx.x * Q
 #pragma unroll
   for (int i = 0; i < Q + HALO; ++i) {
-    const float* row = base + i * PITCH + (i / Q) * 4;
+    const float* row = base + (i + i / Q) * 4;
     float w[2][N4];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -830,11 +847,8 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
       for (int q = 0; q < Q; ++q)
         if (i - q >= 0 && i - q <= HALO && ((i - q) & 1) == h) need = true;
       if (need) {
-#pragma unroll
-        for (int e = 0; e < N4; e += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(row + h * N4 + e);
-          w[h][e] = t.x; w[h][e + 1] = t.y; w[h][e + 2] = t.z; w[h][e + 3] = t.w;
-        }
+        const float4 t = *reinterpret_cast<const float4*>(row + h * UNITS * 4);
+        w[h][0] = t.x; w[h][1] = t.y; w[h][2] = t.z; w[h][3] = t.w;
       }
     }
 #pragma unroll

@@ -1,0 +1,27 @@
+#!/bin/bash
+# Round 2, session d (2 GPUs): every exchange route across processes, bench at N=1 and N=2 (stats / nccl / peer).
+TAG=${1:-r2d}; N=${2:-2}
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+nvidia-smi topo -m > gpurun_out/topo_$TAG.txt 2>&1
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -s > gpurun_out/test_multi_$TAG.log 2>&1; echo "test_multi exit $?"; grep -E "PASS|FAIL|passed|failed|Error" gpurun_out/test_multi_$TAG.log | tail -30
+run() {  # run <gpus> <name> <extra args...>
+  local G=$1; local NAME=$2; shift 2
+  if [ $G -eq 1 ]; then timeout 600 python bench.py --gpus 1 "$@" > gpurun_out/$NAME.json 2> gpurun_out/$NAME.err
+  else NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $G "$@" > gpurun_out/$NAME.json 2> gpurun_out/$NAME.err; fi
+  echo "$NAME exit $?"; python - <<PY
+import json
+for l in open('gpurun_out/$NAME.json'):
+    l = l.strip()
+    if l.startswith('{'):
+        d = json.loads(l)
+        print('$NAME', 'n_gpus', d['n_gpus'], 'value', round(d['value']), 'ms/step', round(d['ms_per_step'], 4), 'e2e', round(d['e2e']['value']), 'parity_ok', d.get('parity_ok'))
+        print('  ', {k: round(v['ms_per_launch'], 4) for k, v in d['kernels'].items() if 'vicreg' in k})
+        print('  ', json.dumps((d.get('parity') or {}).get('exchange')))
+PY
+  tail -2 gpurun_out/$NAME.err
+}
+run 1 bench_g1_$TAG --no-cpu-baseline --no-nonreproducible
+run $N bench_g${N}_stats_$TAG --no-nonreproducible
+run $N bench_g${N}_nccl_$TAG --gather nccl --no-nonreproducible
+run $N bench_g${N}_peer_$TAG --gather peer --no-nonreproducible
+run $N bench_c5_g${N}_$TAG --seconds 30 --batch-per-gpu 512 --steps 20 --warmup 3 --no-nonreproducible
