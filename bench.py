@@ -702,11 +702,29 @@ def run_ours(args):
     # 32-row L2-resident one in reproducible mode) x B sounds.
     voice_bytes = 4.0 * T * B
     achieved = voice_bytes / (va["ms_per_launch"] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum and the issue-side counters of one `ncu --set full` capture of this
-    # kernel (profiles/capture_k_voice_audio.json, written by tools/summarize_ncu.py).  Used only if the capture was
-    # taken from the very sources that are being benchmarked and on this workload shape; null otherwise.
+    # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+    # (profiles/capture_k_voice_audio.json, written by tools/summarize_ncu.py) -- used only if the capture was taken
+    # from the very sources being benchmarked and on this workload shape; null otherwise.
+    # roofline.issue: the kernel is bound by instruction dispatch, not by HBM (SURVEY 8d "report min(HBM, issue)"):
+    # modelled dispatch cycles of its tile loop (tools/issue_model.py, SASS of this build priced with the per-class
+    # costs measured on B200) against what SMs x 4 schedulers x clock offer during the measured launch time.
     traffic, issue, capture_note = None, None, "no capture of this build"
     src = source_hash()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    clk = float((clocks or {}).get("sm_mhz") or 1965.0)
+    try:
+        mdl = json.load(open(os.path.join(harness.ROOT, "profiles", "issue_model.json")))
+        if mdl.get("src_sha256") == src and T % 16 == 0:
+            need = mdl["dispatch_cycles_per_sample"] * float(B) * T / 32.0
+            avail = sms * 4 * clk * 1e6 * (va["ms_per_launch"] * 1e-3)
+            issue = {"instr_per_sample": mdl["instr_per_sample"],
+                     "dispatch_cycles_model": mdl["dispatch_cycles_per_sample"], "achieved_frac": need / avail,
+                     "sm_mhz_used": clk, "schedulers": sms * 4,
+                     "note": "achieved_frac = modelled dispatch cycles of B*T samples / (SMs x 4 schedulers x clock x "
+                             "measured launch time); an upper estimate: the ~11 % of samples in silent tails are zero-"
+                             "filled, not rendered.  Per warp and sample; model and costs: tools/issue_model.py"}
+    except Exception:
+        pass
     try:
         cap = json.load(open(os.path.join(harness.ROOT, "profiles", "capture_k_voice_audio.json")))
         if cap.get("src_sha256") != src:
@@ -717,23 +735,11 @@ def run_ours(args):
         else:
             traffic = cap.get("dram_bytes_per_launch")
             capture_note = "ncu --set full capture %s of this build" % cap.get("run")
-            ipw = cap.get("inst_executed_per_launch")
-            if ipw:
-                # issue roofline (SURVEY 8d "report min(HBM, issue)"): warp instructions per sample from the capture,
-                # the dispatch-cycle cost of that mix (packed fp32 and half-rate ALU instructions hold a
-                # scheduler's dispatch port for two cycles), against what 4 schedulers x SMs x clock offer in the
-                # measured launch time
-                sms = torch.cuda.get_device_properties(dev).multi_processor_count
-                clk = (clocks or {}).get("sm_mhz") or cap.get("sm_mhz") or 1965.0
-                samples = float(B) * T
-                cyc = cap.get("dispatch_cycles_per_warp_instruction", 1.0) * ipw
-                avail = sms * 4 * clk * 1e6 * (va["ms_per_launch"] * 1e-3)
-                issue = {"instr_per_sample": ipw * 32.0 / samples, "warp_instructions_per_launch": ipw,
-                         "dispatch_cycles_model": cyc * 32.0 / samples, "achieved_frac": cyc / avail,
-                         "issue_slots_busy_pct_ncu": cap.get("issue_active_pct"),
-                         "pipes_pct_ncu": cap.get("pipes_pct"), "sm_mhz_used": clk,
-                         "note": "achieved_frac = modelled dispatch cycles / (SMs x 4 schedulers x clock x measured "
-                                 "launch time); instr_per_sample counts warp instructions x 32 lanes / samples"}
+            if issue is not None:
+                issue["ncu"] = {k: cap.get(k) for k in ("inst_executed_per_launch", "issue_active_pct", "pipes_pct",
+                                                        "gpu_time_us")}
+                if cap.get("inst_executed_per_launch"):
+                    issue["ncu"]["instr_per_sample_executed"] = cap["inst_executed_per_launch"] * 32.0 / (float(B) * T)
     except Exception:
         pass
     line = {

@@ -699,7 +699,11 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
       float x1[SPT], x2[SPT], srcs[SPT];
       const float4 r0 = __ldg(rj + 0);
       const float4 r1 = __ldg(rj + 1);
+#ifdef IAS_AUDIO_COUNT_NOCLAMP_ONLY  // tools/issue_model.py: object for instruction counting only (never shipped)
+      if (true)
+#else
       if (noclamp)
+#endif
         pitch_pass<SPT, VEC, false>(x1, x2, srcs, r0, r1, ft0, scale, fj, fj1, midi1, depth1, midi2, depth2, A.sr, A.rsr,
                                     t0, T);
       else

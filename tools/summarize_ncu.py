@@ -48,6 +48,43 @@ def raw_page(rep):
     return {h: (u, v) for h, u, v in zip(head, units, vals)}
 
 
+def write_capture_json(tag, m, rep_name):
+    """profiles/capture_k_voice_audio.json: what bench.py's roofline.traffic / roofline.issue.ncu quote, tied to the
+    source hash of the session's own bench line (a capture of other sources is ignored by bench.py)."""
+    def val(k, default=None):
+        try:
+            return float(m[k][1].replace(",", ""))
+        except Exception:
+            return default
+
+    src, B, T = None, 1024, 176400
+    for cand in (f"bench_{tag}.json", f"plain_{tag}.log"):
+        try:
+            for line in open(os.path.join(OUT, cand)):
+                if line.startswith("{"):
+                    d = json.loads(line)
+                    src = d.get("src_sha256")
+                    B = d["config"]["per_gpu_batch"]
+                    T = int(d["config"]["seconds"] * 44100)
+        except Exception:
+            pass
+        if src:
+            break
+    rd = val("dram__bytes_read.sum", 0.0) * UNIT_BYTES.get(m.get("dram__bytes_read.sum", ("byte",))[0], 1)
+    wr = val("dram__bytes_write.sum", 0.0) * UNIT_BYTES.get(m.get("dram__bytes_write.sum", ("byte",))[0], 1)
+    out = {
+        "run": tag, "capture": rep_name, "src_sha256": src, "B": B, "T": T,
+        "dram_bytes_per_launch": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr),
+        "gpu_time_us": val("gpu__time_duration.sum"),
+        "inst_executed_per_launch": val("smsp__inst_executed.sum"),
+        "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "pipes_pct": {p: val(f"sm__inst_executed_pipe_{p}.avg.pct_of_peak_sustained_active") for p in ("fma", "alu", "xu", "lsu")},
+        "fp64_pct": val("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+        "registers": val("launch__registers_per_thread"),
+    }
+    json.dump(out, open(os.path.join(PROF, "capture_k_voice_audio.json"), "w"), indent=1)
+
+
 def full_summaries(tag):
     lines = [f"# ncu --set full summaries, run {tag} (B200, bench.py --steps 3 --warmup 3 --no-cpu-baseline, "
              "one launch per kernel)\n"]
@@ -72,6 +109,8 @@ def full_summaries(tag):
         stalls.sort(reverse=True)
         lines.append("top stall reasons (warps per issue-active cycle): " +
                      ", ".join(f"{n}={v:.2f}" for v, n in stalls[:7]))
+        if "k_voice_audio" in name:
+            write_capture_json(tag, m, os.path.basename(rep))
         try:
             rd = float(m["dram__bytes_read.sum"][1]) * UNIT_BYTES[m["dram__bytes_read.sum"][0]]
             wr = float(m["dram__bytes_write.sum"][1]) * UNIT_BYTES[m["dram__bytes_write.sum"][0]]
