@@ -681,9 +681,18 @@ def run_ours(args):
     parity, parity_failures = (None, [])
     if not args.no_parity:
         parity, parity_failures = parity_block(args, rank, world, dev, voice, gram, vic, wa, wp)
-    if rank != 0:
+    def teardown():
+        # graphs that captured collectives (--gather nccl) must be gone before the communicator is, and every rank
+        # leaves together: rank 0 is still busy with the CPU oracle of the parity block while the others are done
+        nonlocal graph_v, graph
+        graph_v = graph = None
         if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
         return
 
     sounds = B * world * args.steps
@@ -816,8 +825,7 @@ def run_ours(args):
                       "oracle/ (torch fp32 Voice restatement -> torch conv1d PQMF -> bridge -> torch VICReg ops)",
             "ms_per_step": ms, "stage_ms": stage}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
     if parity_failures:
         print("bench.py: PARITY FAILED: " + "; ".join(parity_failures), file=sys.stderr)
         sys.exit(3)

@@ -819,7 +819,10 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// grid = any (grid-stride over float4 items of the packet), block = 256
+// block = 256 = 64 float4 items of the packet x 4 cooperating lanes: lane j of an item adds up the K-split partials
+// (or variance partials) j, j + 4, ... with all its loads in flight at once, two shuffle steps finish the sum in a fixed
+// order, and lane j stores the result to peers j, j + 4, ...  grid = ceil(items / 64).
+constexpr int PUB_PARTS = 4;
 __global__ void __launch_bounds__(256) k_stats_publish(const float* __restrict__ gram_partial,
                                                        const float* __restrict__ varpart,
                                                        const float* __restrict__ mean, int D, int Dp, int ntiles,
@@ -829,19 +832,23 @@ __global__ void __launch_bounds__(256) k_stats_publish(const float* __restrict__
   const size_t pf = packet_floats(Dp, ntiles);
   const size_t slot = XCHG_HDR_FLOATS + ((size_t)rank * 2 + (epoch & 1)) * pf;
   const int n4 = (int)(pf / 4);
-  for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
-    const int f = i4 * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int part = threadIdx.x & (PUB_PARTS - 1);
+  const int i4 = blockIdx.x * (256 / PUB_PARTS) + (threadIdx.x >> 2);
+  const int f = i4 * 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i4 < n4) {
     if (f < 2 * Dp) {  // local column means, [2][Dp]
       const int s = f / Dp, d = f - s * Dp;
-      float t[4];
+      if (part == 0) {
+        float t[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) t[e] = (d + e < D) ? mean[s * D + d + e] : 0.0f;
-      v = make_float4(t[0], t[1], t[2], t[3]);
+        for (int e = 0; e < 4; ++e) t[e] = (d + e < D) ? mean[s * D + d + e] : 0.0f;
+        v = make_float4(t[0], t[1], t[2], t[3]);
+      }
     } else if (f < 4 * Dp) {  // locally-centred second moments, [2][Dp]: sum of the NV k_center_pack partials
       const int g = f - 2 * Dp, s = g / Dp, d = g - s * Dp;
       float t[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int p = 0; p < NV; ++p)
+      for (int p = part; p < NV; p += PUB_PARTS)
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           if (d + e < D) t[e] += varpart[((size_t)p * 2 + s) * D + d + e];
@@ -850,22 +857,30 @@ __global__ void __launch_bounds__(256) k_stats_publish(const float* __restrict__
       const size_t g = (size_t)f - 4 * Dp;
       const size_t st = g / (TILE * TILE), e = g - st * (TILE * TILE);  // st = s * ntiles + t
       const float4* src = reinterpret_cast<const float4*>(gram_partial + st * splits * TILE * TILE + e);
-      int k = 0;
-      for (; k + 4 <= splits; k += 4) {  // four partial tiles in flight
-        const float4 a0 = src[(size_t)(k + 0) * (TILE * TILE / 4)], a1 = src[(size_t)(k + 1) * (TILE * TILE / 4)];
-        const float4 a2 = src[(size_t)(k + 2) * (TILE * TILE / 4)], a3 = src[(size_t)(k + 3) * (TILE * TILE / 4)];
-        v.x += a0.x; v.y += a0.y; v.z += a0.z; v.w += a0.w;
-        v.x += a1.x; v.y += a1.y; v.z += a1.z; v.w += a1.w;
-        v.x += a2.x; v.y += a2.y; v.z += a2.z; v.w += a2.w;
-        v.x += a3.x; v.y += a3.y; v.z += a3.z; v.w += a3.w;
+      constexpr int U = 4;  // up to 16 splits: every load of a lane is in flight at once
+      int k = part;
+      for (; k + (U - 1) * PUB_PARTS < splits; k += U * PUB_PARTS) {
+        float4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = src[(size_t)(k + u * PUB_PARTS) * (TILE * TILE / 4)];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { v.x += a[u].x; v.y += a[u].y; v.z += a[u].z; v.w += a[u].w; }
       }
-      for (; k < splits; ++k) {
+      for (; k < splits; k += PUB_PARTS) {
         const float4 a = src[(size_t)k * (TILE * TILE / 4)];
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
       }
     }
-    for (int q = 0; q < world; ++q) *reinterpret_cast<float4*>(peers.base[q] + slot + f) = v;
   }
+#pragma unroll
+  for (int o = 1; o < PUB_PARTS; o <<= 1) {  // lanes of an item are adjacent: fixed-order tree, every lane gets the sum
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  if (i4 < n4)
+    for (int q = part; q < world; q += PUB_PARTS) *reinterpret_cast<float4*>(peers.base[q] + slot + f) = v;
   // last CTA done: every CTA's packet stores are ordered before its arrival, the last arrival publishes the flag
   __threadfence_system();
   __syncthreads();
@@ -1322,7 +1337,7 @@ extern "C" int ias_vicreg_loss_stats_stages(const float* x, const float* y, floa
   const size_t pf = packet_floats(p.Dp, p.ntiles);
   if (do_publish) {
     ProfScope prof_(K_VICREG_STATS_PUBLISH, st);
-    const int grid = (int)((pf / 4 + 255) / 256);
+    const int grid = (int)((pf / 4 + 256 / PUB_PARTS - 1) / (256 / PUB_PARTS));
     k_stats_publish<<<grid, 256, 0, st>>>(w + p.off_gram, w + p.off_varpart, w + p.off_mean, D, p.Dp, p.ntiles, p.splits,
                                           p.NV, peers, world, rank);
   }
