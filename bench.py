@@ -57,7 +57,12 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=128,
                     help="sounds per CPU chunk (BASELINE configs[0]: 128); the reference arm renders --batch-per-gpu "
                          "sounds per step in chunks of this size, the in-run cpu_baseline leg one chunk per step")
-    ap.add_argument("--no-nonreproducible", action="store_true", help="skip the reproducible=False e2e variant")
+    ap.add_argument("--reproducible", action="store_true",
+                    help="SynthConfig(reproducible=True): noise rows repeat with period 32, so the table (22.6 MB) lives in "
+                         "L2.  Default is the reference's own setting, reproducible: False (conf/config.yaml:38): a [B,T] "
+                         "noise table (722 MB at 1024 x 4 s) that the render streams from HBM every step")
+    ap.add_argument("--no-nonreproducible", "--no-noise-variant", dest="no_noise_variant", action="store_true",
+                    help="skip the e2e variant with the other noise mode")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (outside the timed region)")
     ap.add_argument("--parity-sounds", type=int, default=0,
                     help="sounds of the parity block's CPU oracle render (default: 128 at 4 s, 16 for long clips)")
@@ -182,7 +187,8 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # CPU reference arm / baseline (oracle on the host cores)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_step_rate(chunk: int, bands: int, seconds: float, steps: int, warmup: int, sounds_per_step: int = 0):
+def cpu_step_rate(chunk: int, bands: int, seconds: float, steps: int, warmup: int, sounds_per_step: int = 0,
+                  reproducible: bool = False):
     """Oracle front end on the host cores.  One step = `sounds_per_step` sounds (default: one chunk) rendered and
     filtered in chunks of `chunk` sounds (bounds the host memory: the torch restatement of the synth keeps ~25
     [chunk, T] fp32 intermediates alive), then the bridge projections and ONE VICReg loss over the step's embeddings.
@@ -204,7 +210,7 @@ def cpu_step_rate(chunk: int, bands: int, seconds: float, steps: int, warmup: in
             # chunk c of step i = batch number i * nchunks + c of a batch-size-`chunk` Voice: the same sound ids as one
             # batch of `sounds_per_step` sounds (ids are batch_idx * B + row) when chunk divides it
             r = harness.oracle_front_end(i * nchunks + c, n, N=bands, seconds=seconds, timings=tc, torch_ops=True,
-                                         cfg_batch=sounds_per_step)
+                                         cfg_batch=sounds_per_step, reproducible=reproducible)
             xs.append(r["x"])
             ys.append(r["y"])
             for k, v in tc.items():
@@ -235,7 +241,7 @@ def run_reference(args):
         return
     per_step = args.batch_per_gpu
     value, ms, stage = cpu_step_rate(args.cpu_sample, args.bands, args.seconds, args.steps, args.warmup,
-                                     sounds_per_step=per_step)
+                                     sounds_per_step=per_step, reproducible=args.reproducible)
     cores = torch.get_num_threads()
     sample = (f"{per_step} sounds x {args.seconds:g} s per step in chunks of {args.cpu_sample} (BASELINE configs[0] is one "
               f"chunk), oracle/ CPU path: torch fp32 Voice restatement -> torch conv1d PQMF -> bridge -> torch VICReg ops "
@@ -320,9 +326,11 @@ def parity_block(args, rank, world, dev, voice, gram, vic, wa, wp):
             failures.append("exchange loss4_rel %s identical=%s" % (rel, same))
         # ---- rank 0: a small batch against the CPU oracle ----
         P = args.parity_sounds or (128 if args.seconds <= 4.0 else 16)
-        Bv = (P + 31) // 32 * 32  # reproducible mode renders multiples of 32; the first P rows are compared
-        ref = harness.oracle_front_end(0, P, N=args.bands, seconds=args.seconds, cfg_batch=P)
-        cfgP = ias_b200.SynthConfig(batch_size=Bv, reproducible=True, sample_rate=44100,
+        # reproducible mode renders multiples of 32 (the first P rows are compared); same noise mode as the timed run
+        Bv = (P + 31) // 32 * 32 if args.reproducible else P
+        ref = harness.oracle_front_end(0, P, N=args.bands, seconds=args.seconds, cfg_batch=P,
+                                       reproducible=args.reproducible)
+        cfgP = ias_b200.SynthConfig(batch_size=Bv, reproducible=args.reproducible, sample_rate=44100,
                                     buffer_size_seconds=args.seconds)
         vP = ias_b200.Voice(synthconfig=cfgP).to(dev)
         vcfg = types.SimpleNamespace(dim=D, embeddim=D, vicreg=types.SimpleNamespace(
@@ -386,7 +394,8 @@ def run_ours(args):
 
     B = args.batch_per_gpu
     T = int(args.seconds * 44100)
-    cfg = ias_b200.SynthConfig(batch_size=B, reproducible=True, sample_rate=44100, buffer_size_seconds=args.seconds)
+    cfg = ias_b200.SynthConfig(batch_size=B, reproducible=args.reproducible, sample_rate=44100,
+                               buffer_size_seconds=args.seconds)
     voice = ias_b200.Voice(synthconfig=cfg).to(dev)
     gram = ias_b200.PQMF(N=args.bands).to(dev)
     vcfg = types.SimpleNamespace(dim=D, embeddim=D, vicreg=types.SimpleNamespace(
@@ -637,10 +646,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_params_ms = float(t.item())
 
-    # ---- variant: the reference's own noise mode, reproducible=False: a [B,T] table read from HBM every step ----
+    # ---- variant: the other noise mode (default run: reproducible=True, the 32-row L2-resident table) ----
     e2e_nr_ms, nr_mode = None, None
-    if not args.no_nonreproducible:
-        cfg_nr = ias_b200.SynthConfig(batch_size=B, reproducible=False, sample_rate=44100,
+    if not args.no_noise_variant:
+        cfg_nr = ias_b200.SynthConfig(batch_size=B, reproducible=not args.reproducible, sample_rate=44100,
                                       buffer_size_seconds=args.seconds)
         voice_nr = ias_b200.Voice(synthconfig=cfg_nr).to(dev)
 
@@ -707,9 +716,11 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     scale_T = T / T_4S
     va = kern.get("k_voice_audio", {"ms_per_launch": float("nan"), "launches": 0})
-    # dominant kernel: k_voice_audio.  Algorithmic bytes per launch = 4*T written per sound (noise table is the
-    # 32-row L2-resident one in reproducible mode) x B sounds.
-    voice_bytes = 4.0 * T * B
+    # dominant kernel: k_voice_audio.  Algorithmic bytes per launch: 4*T audio written per sound, plus
+    # 4*T noise read per sound when the noise table is the reference's [B,T] one (reproducible=False: 722 MB, streamed
+    # from HBM); with the 32-row reproducible table the noise is L2 resident and not counted.
+    noise_bytes = 0.0 if args.reproducible else 4.0 * T * B
+    voice_bytes = 4.0 * T * B + noise_bytes
     achieved = voice_bytes / (va["ms_per_launch"] * 1e-3) / 1e9
     # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
     # (profiles/capture_k_voice_audio.json, written by tools/summarize_ncu.py) -- used only if the capture was taken
@@ -768,8 +779,10 @@ def run_ours(args):
             "workload": workload_name(args.bands, args.seconds, B, world, exchange_desc),
             "per_gpu_batch": B, "global_batch": B * world, "seconds": args.seconds, "bands": args.bands,
             "exchange": args.gather if world > 1 else None,
-            "noise": "reproducible (32-row table, L2 resident); the reference's reproducible=False ([B,T] table read "
-                     "from HBM) is timed beside it as e2e_nonreproducible",
+            "noise": ("reproducible=True: 32-row table, L2 resident" if args.reproducible else
+                      "reproducible=False, the reference's setting (conf/config.yaml:38): [B,T] noise table, %.0f MB "
+                      "streamed from HBM every step" % (4e-6 * B * T)) + "; the other mode is timed beside it as "
+                                                                            "e2e_noise_variant",
             "l2": "inputs larger than L2: %.0f MB audio + %.0f MB bands per step vs 126 MB L2" % (
                 4e-6 * B * T, 4e-6 * B * T),
             "bridge": "abs-mean pool to 256 bins + 2 torch matmuls (harness, not a reference component), inside the "
@@ -782,10 +795,15 @@ def run_ours(args):
             "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": capture_note, "issue": issue,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": voice_bytes,
+            "algorithmic_bytes_note": "4*T*B audio written" + ("" if args.reproducible else
+                                                               " + 4*T*B noise read ([B,T] table, larger than L2)"),
+            "frac_audio_write_only": 4.0 * T * B / (va["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
             "ms_per_launch": va["ms_per_launch"],
             "note": "k_voice_audio is instruction-issue bound, not HBM bound (DESIGN.md); step-level fraction below",
             "step_frac": value / world * ALGO_BYTES_PER_SOUND * scale_T / 1e9 / hbm_peak,
             "step_algorithmic_bytes_per_sound": ALGO_BYTES_PER_SOUND * scale_T,
+            "step_frac_with_noise_read": (None if args.reproducible else
+                                          value / world * (ALGO_BYTES_PER_SOUND * scale_T + 4.0 * T) / 1e9 / hbm_peak),
         },
         "kernels": kern,
         "e2e": {"value": sounds / (e2e_ms * 1e-3), "unit": "sounds/s", "h2d_bytes_per_step": 8,
@@ -797,11 +815,12 @@ def run_ours(args):
         "e2e_host_params": {"value": sounds / (e2e_params_ms * 1e-3), "unit": "sounds/s",
                             "h2d_bytes_per_step": 78 * B * 4, "d2h_bytes_per_step": 16,
                             "note": "same, but the [78,B] parameter block comes from pinned host memory every step"},
-        "e2e_nonreproducible": (None if e2e_nr_ms is None else {
+        "e2e_noise_variant": (None if e2e_nr_ms is None else {
             "value": sounds / (e2e_nr_ms * 1e-3), "unit": "sounds/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 16,
-            "mode": nr_mode, "note": "same step with SynthConfig(reproducible=False), the reference's setting "
-                                     "(conf/config.yaml:38): noise is a [B,T] table (%.0f MB) streamed from HBM" % (
-                                         4e-6 * B * T)}),
+            "mode": nr_mode, "reproducible": not args.reproducible,
+            "note": "same step with SynthConfig(reproducible=%s): %s" % (
+                not args.reproducible, "32-row noise table, L2 resident" if not args.reproducible else
+                "[B,T] noise table streamed from HBM")}),
         "parity": parity,
         "parity_ok": not parity_failures,
         "src_sha256": src,
@@ -818,7 +837,8 @@ def run_ours(args):
         # bounded sample: 30 steps x 128 four-second sounds (16 thirty-second ones), about 10 s of host work
         cpu_steps = 30
         chunk = args.cpu_sample if args.seconds <= 4.0 else max(8, int(args.cpu_sample * 4.0 / args.seconds) // 8 * 8)
-        v, ms, stage = cpu_step_rate(chunk, args.bands, args.seconds, steps=cpu_steps, warmup=2)
+        v, ms, stage = cpu_step_rate(chunk, args.bands, args.seconds, steps=cpu_steps, warmup=2,
+                                     reproducible=args.reproducible)
         line["cpu_baseline"] = {
             "value": v, "unit": "sounds/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{chunk} sounds x {args.seconds:g} s per step x {cpu_steps} steps (BASELINE configs[0]) through "
