@@ -725,9 +725,9 @@ def run_ours(args):
     # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
     # (profiles/capture_k_voice_audio.json, written by tools/summarize_ncu.py) -- used only if the capture was taken
     # from the very sources being benchmarked and on this workload shape; null otherwise.
-    # roofline.issue: the kernel is bound by instruction dispatch, not by HBM (SURVEY 8d "report min(HBM, issue)"):
-    # modelled dispatch cycles of its tile loop (tools/issue_model.py, SASS of this build priced with the per-class
-    # costs measured on B200) against what SMs x 4 schedulers x clock offer during the measured launch time.
+    # roofline.issue: the kernel is bound on the instruction side, not by HBM (SURVEY 8d "report min(HBM, issue)"):
+    # cycles its tile loop needs on the busiest execution pipe (tools/issue_model.py: SASS of this build priced with the
+    # pipe occupancies measured on B200) against what SMs x 4 schedulers x clock offer during the measured launch time.
     traffic, issue, capture_note = None, None, "no capture of this build"
     src = source_hash()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -735,14 +735,17 @@ def run_ours(args):
     try:
         mdl = json.load(open(os.path.join(harness.ROOT, "profiles", "issue_model.json")))
         if mdl.get("src_sha256") == src and T % 16 == 0:
-            need = mdl["dispatch_cycles_per_sample"] * float(B) * T / 32.0
+            need = mdl["bound_cycles_per_sample"] * float(B) * T / 32.0
             avail = sms * 4 * clk * 1e6 * (va["ms_per_launch"] * 1e-3)
-            issue = {"instr_per_sample": mdl["instr_per_sample"],
-                     "dispatch_cycles_model": mdl["dispatch_cycles_per_sample"], "achieved_frac": need / avail,
+            issue = {"instr_per_sample": mdl["instr_per_sample"], "pipe_cycles_per_sample": mdl["pipe_cycles_per_sample"],
+                     "bound_pipe": mdl["bound_pipe"], "bound_cycles_per_sample": mdl["bound_cycles_per_sample"],
+                     "achieved_frac": need / avail, "cycles_per_sample_measured": avail / (float(B) * T / 32.0),
                      "sm_mhz_used": clk, "schedulers": sms * 4,
-                     "note": "achieved_frac = modelled dispatch cycles of B*T samples / (SMs x 4 schedulers x clock x "
-                             "measured launch time); an upper estimate: the ~11 % of samples in silent tails are zero-"
-                             "filled, not rendered.  Per warp and sample; model and costs: tools/issue_model.py"}
+                     "note": "achieved_frac = cycles the busiest pipe (FMA) needs for B*T samples / (SMs x 4 schedulers x "
+                             "clock x measured launch time); an upper estimate: the ~11 % of samples in silent tails are "
+                             "zero-filled, not rendered.  The pipes overlap (tools/micro/dispatch_mix.cu), so 1.0 would be "
+                             "a kernel limited only by FMA-pipe throughput; the rest is dependent-issue latency at 4 warps "
+                             "per scheduler (DESIGN.md 3.1).  Per warp and sample; model: tools/issue_model.py"}
     except Exception:
         pass
     try:
@@ -799,7 +802,8 @@ def run_ours(args):
                                                                " + 4*T*B noise read ([B,T] table, larger than L2)"),
             "frac_audio_write_only": 4.0 * T * B / (va["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
             "ms_per_launch": va["ms_per_launch"],
-            "note": "k_voice_audio is instruction-issue bound, not HBM bound (DESIGN.md); step-level fraction below",
+            "note": "k_voice_audio is bound on the instruction side (dependent-issue latency at 4 warps per scheduler, see `issue`), "
+                    "not by HBM (DESIGN.md 3.1); step-level fraction below",
             "step_frac": value / world * ALGO_BYTES_PER_SOUND * scale_T / 1e9 / hbm_peak,
             "step_algorithmic_bytes_per_sound": ALGO_BYTES_PER_SOUND * scale_T,
             "step_frac_with_noise_read": (None if args.reproducible else

@@ -128,6 +128,15 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
   return v;
 }
 
+[[maybe_unused]] __device__ __forceinline__ float warp_incl_scan(float v, int lane) {  // (ablation builds only)
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // k_voice_control
 // ------------------------------------------------------------------------------------------------------------
@@ -498,6 +507,9 @@ __device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
 // vm::vco_increment for two samples: 2*pi*hz(clamp(midi + depth*mod, 0, 127)) / sample_rate, same op order.
 template <bool CLAMP>
 __device__ __forceinline__ P2 vco_increment_p2(float midi, float depth, P2 mod, float sr, float rsr) {
+#if IAS_ABL_NOPASS1
+  return p2_fma(p2b(depth * rsr), mod, p2b(midi * rsr));
+#endif
   // depth * mod must keep its own rounding (see the note on contraction above): issued as fma(depth, mod, +0.0),
   // which ptxas can neither fold into a multiply (a -0 product would change sign) nor contract with the add
   P2 m = p2_add(p2b(midi), p2_fma(p2b(depth), mod, p2b(0.0f)));
@@ -536,6 +548,26 @@ __device__ __forceinline__ P2 vco_increment_p2(float midi, float depth, P2 mod, 
   const P2 nneg = p2_sub(p2b(magic), t);  // -rint(a / pi)
   f = p2_fma(a, p2b(C2), p2_fma(a, p2b(C1), nneg));
 }
+// ---- ablation switches: DIAGNOSTIC variant builds only (tools/gpu_ablate.sh); they change the results on purpose to
+// show what each part of the tile loop costs.  Never defined in the shipped library.
+#ifndef IAS_ABL_NOXU     // SFU cosines / ex2 / rcp of the oscillators replaced by one FMA each
+#define IAS_ABL_NOXU 0
+#endif
+#ifndef IAS_ABL_NOPASS1  // the bit-exact pitch -> increment chain replaced by one FMA
+#define IAS_ABL_NOPASS1 0
+#endif
+#ifndef IAS_ABL_NOF64    // phase accumulated in fp32: no fp32<->fp64 conversions, no DADD
+#define IAS_ABL_NOF64 0
+#endif
+#ifndef IAS_ABL_NOBAR    // no CTA barrier / cross-warp carry (each warp scans alone)
+#define IAS_ABL_NOBAR 0
+#endif
+#if IAS_ABL_NOXU
+#define IAS_COS(x) fmaf((x), (x), -1.0f)
+#else
+#define IAS_COS(x) __cosf(x)
+#endif
+
 // Oscillator arguments are reduced in RADIANS with a two-constant Cody-Waite step: n = rint(a / P) from one FMA against
 // the 1.5 * 2^23 magic constant, then y = fma(-n, P_hi, a) (exact product, ONE rounding relative to the small result,
 // so accuracy near the zeros of sin is kept) and y = fma(-n, P_lo, y) (P_lo = P - P_hi, |n P_lo| <= 0.07 for 30 s
@@ -553,7 +585,7 @@ __device__ __forceinline__ P2 cos_arg_p2(P2 a) {
   const P2 t = p2_fma(a, p2b(C1), p2b(magic));
   const P2 nneg = p2_sub(p2b(magic), t);                          // -rint(a / (2 pi)), exact
   const P2 y = p2_fma(nneg, p2b(P_LO), p2_fma(nneg, p2b(P_HI), a));
-  return p2(__cosf(p2lo(y)), __cosf(p2hi(y)));
+  return p2(IAS_COS(p2lo(y)), IAS_COS(p2hi(y)));
 #else
   const float C1 = 0.159154936671257019f;                                              // (float)(1/(2 pi))
   const float C2 = (float)(0.15915494309189533577 - (double)0.159154936671257019f);    // 1/(2 pi) - C1
@@ -601,13 +633,21 @@ __device__ __forceinline__ P2 squaresaw_core_p2(P2 a, float pk, float shape) {
   const P2 fr = p2_mul(f, p2b(IAS_PI_F));
 #endif
   float e0, e1, r0, r1;
+#if IAS_ABL_NOXU
+  e0 = fmaf(p2lo(sc), 0.5f, 1.0f); e1 = fmaf(p2hi(sc), 0.5f, 1.0f);
+#else
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(p2lo(sc)));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(p2hi(sc)));
+#endif
   const P2 ep = p2_add(p2(e0, e1), p2b(1.0f));
+#if IAS_ABL_NOXU
+  r0 = fmaf(p2lo(ep), -0.25f, 1.0f); r1 = fmaf(p2hi(ep), -0.25f, 1.0f);
+#else
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p2lo(ep)));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p2hi(ep)));
+#endif
   const P2 th = p2_fma(p2b(-2.0f), p2(r0, r1), p2b(1.0f));
-  const P2 c = p2(__cosf(p2lo(fr)), __cosf(p2hi(fr)));
+  const P2 c = p2(IAS_COS(p2lo(fr)), IAS_COS(p2hi(fr)));
   return p2_mul(th, p2_fma(p2b(shape), c, p2(parity_sign(p2lo(t)), parity_sign(p2hi(t)))));
 }
 
@@ -654,7 +694,12 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
   constexpr bool PREFETCH = IAS_AUDIO_PREFETCH != 0;
   constexpr int TILE = NT * SPT;
   constexpr int NW = NT / 32;
-  __shared__ double s_wsum[2][2][NW];  // [buffer][vco][warp]
+#if IAS_ABL_NOF64
+  using acc_t = float;
+#else
+  using acc_t = double;
+#endif
+  __shared__ acc_t s_wsum[2][2][NW];  // [buffer][vco][warp]
   __shared__ float s_peak[NW];
   __shared__ int s_slot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -677,7 +722,7 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
     float* out = A.audio + (size_t)b * T;
     const int ntiles = A.ntiles[b];
 
-    double carry1 = 0.0, carry2 = 0.0;
+    acc_t carry1 = 0, carry2 = 0;
     float tpeak = 0.0f;
     float ft0 = (float)(tid * SPT);  // float(index of the thread's first sample); exact, advanced by TILE per tile
     for (int tile = 0; tile < ntiles; ++tile, ft0 += (float)TILE) {
@@ -710,14 +755,14 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
         pitch_pass<SPT, VEC, true>(x1, x2, srcs, r0, r1, ft0, scale, fj, fj1, midi1, depth1, midi2, depth2, A.sr, A.rsr,
                                    t0, T);
       // ---- block scan -------------------------------------------------------------------------------------
-      double tot1 = 0.0, tot2 = 0.0;
+      acc_t tot1 = 0, tot2 = 0;
 #pragma unroll
       for (int k = 0; k < SPT; ++k) {
-        tot1 += (double)x1[k];
-        tot2 += (double)x2[k];
+        tot1 += (acc_t)x1[k];
+        tot2 += (acc_t)x2[k];
       }
-      const double inc1 = warp_incl_scan(tot1, lane);
-      const double inc2 = warp_incl_scan(tot2, lane);
+      const acc_t inc1 = warp_incl_scan(tot1, lane);
+      const acc_t inc2 = warp_incl_scan(tot2, lane);
       if (lane == 31) {
         s_wsum[buf][0][warp] = inc1;
         s_wsum[buf][1][warp] = inc2;
@@ -741,11 +786,13 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
 #pragma unroll
         for (int k = 0; k < SPT; ++k) nzv[k] = (t0 + k) < T ? __ldg(nz + t0 + k) : 0.0f;
       }
+#if !IAS_ABL_NOBAR
       __syncthreads();
-      double acc1 = carry1 + (inc1 - tot1), acc2 = carry2 + (inc2 - tot2);
+#endif
+      acc_t acc1 = carry1 + (inc1 - tot1), acc2 = carry2 + (inc2 - tot2);
 #pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const double w1 = s_wsum[buf][0][w], w2 = s_wsum[buf][1][w];
+      for (int w = 0; w < (IAS_ABL_NOBAR ? 0 : NW); ++w) {
+        const acc_t w1 = s_wsum[buf][0][w], w2 = s_wsum[buf][1][w];
         if (w < warp) {
           acc1 += w1;
           acc2 += w2;
@@ -762,13 +809,13 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
         const P2 u = p2_sub(sp, p2b(fj));
         const P2 um = p2_sub(sp, p2b(fj1));
         const P2 r = p2(fmaxf(p2lo(um), 0.0f), fmaxf(p2hi(um), 0.0f));
-        acc1 += (double)x1[k];
+        acc1 += (acc_t)x1[k];
         const float a10 = (float)acc1;
-        acc1 += (double)x1[k + 1];
+        acc1 += (acc_t)x1[k + 1];
         const float a11 = (float)acc1;
-        acc2 += (double)x2[k];
+        acc2 += (acc_t)x2[k];
         const float a20 = (float)acc2;
-        acc2 += (double)x2[k + 1];
+        acc2 += (acc_t)x2[k + 1];
         const float a21 = (float)acc2;
         const P2 arg1 = p2_add(p2(a10, a11), p2b(phase1));
         const P2 arg2 = p2_add(p2(a20, a21), p2b(phase2));
