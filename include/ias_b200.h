@@ -144,8 +144,10 @@ IAS_API int ias_pqmf_analysis_image(const float* x, const float* H_dev, const fl
 /* PQMF.analysis plus pooled band magnitudes -- harness bridge of SURVEY.md 8(d), not a reference surface:
  * feat[b][i] = mean |bands_flat[b][floor(i S/P) .. ceil((i+1) S/P))| with S = N*L, i.e.
  * torch.nn.functional.adaptive_avg_pool1d(out.abs().reshape(B,1,N*L), P), accumulated by the analysis CTAs while the
- * band values are in registers (per-CTA partial sums in `workspace`, then a small fixed-order finalize kernel), so the
- * bands are written once and not read back.  Requires a specialised kernel (N in {2,3,4,8,16}, K = 63, H_host given)
+ * band values are in registers: every warp adds its |values| in 2^-22 fixed point (one redux.sync) into 64-bit bin
+ * accumulators in `workspace` (integer adds: bit-identical from run to run whatever the arrival order), a small
+ * finalize kernel converts and divides -- so the bands are written once and not read back.  Resolution 2.4e-7 per
+ * thread sum; a thread's sum over its steps saturates at 32 (never reached for audio within [-1, 1]).  Requires a specialised kernel (N in {2,3,4,8,16}, K = 63, H_host given)
  * and bins wider than its CTA tile; returns IAS_ERR_UNSUPPORTED otherwise (callers then pool with ias_abs_avg_pool).
  * workspace >= ias_pqmf_pool_workspace_bytes(B, T, N, K) bytes of device memory. */
 IAS_API size_t ias_pqmf_pool_workspace_bytes(int B, int T, int N, int K);

@@ -106,17 +106,23 @@ struct BandNorm {
 // while a CTA still holds its band values in registers it adds up |value| per pooling bin.  A CTA's TILE_N steps of one
 // band are TILE_N consecutive elements of the flattened [N*L] axis; with TILE_N + 1 <= floor(N*L / P) they touch at
 // most two bins, ilo = floor(first * P / (N*L)) and ilo + 1 (torch's bins [floor(i S/P), ceil((i+1) S/P)) overlap by
-// up to one element, which then counts for both).  The CTA writes the two sums to partial[b][k][tile][2] in a fixed
-// order (warp shuffle tree, then warps in order); k_pool_finalize adds each bin's few partials -- deterministic, and
-// the bands are not read back from HBM.
+// up to one element, which then counts for both).  Every warp adds its 32*Q values in 2^-22 fixed point (one
+// redux.sync) into the 64-bit accumulators acc[b][ilo], acc[b][ilo + 1] (red.global.add.u64; integer adds commute, so
+// the result is bit-identical from run to run); k_pool_finalize_fixed converts and divides by the bin width.  The bands
+// are not read back from HBM.  (Round 1 reduced per-CTA float partials through shared memory in a fixed order: same
+// determinism, one barrier, a second phase and ~80 more instructions per thread: 0.333 vs 0.3265 ms.)
 struct PoolReq {  // host-side request of the pooled epilogue
   float* feat;  // [B][P]
   int P;
   void* workspace;
   size_t workspace_bytes;
 };
+#define IAS_POOL_SCALE 4194304.0f  /* 2^22: fixed-point resolution of the pooled sums */
+// a thread's contribution saturates at 2^27 - 1 (a sum of 32 over its Q steps) so that a warp's 32 contributions cannot
+// wrap 32 bits; bands of audio within [-1, 1] stay below sum_j |H[k][j]| < 2 per step
+__device__ __forceinline__ unsigned pool_fixed(float t) { return min(__float2uint_rn(t * IAS_POOL_SCALE), 134217727u); }
 struct PoolArgs {
-  float* partial;  // [B][N][tiles][2]
+  unsigned long long* acc;  // [B][P] fixed-point bin accumulators, zeroed by the launcher
   int P;
   int S;  // N * L  (S * P < 2^31 is checked by the caller)
   // floor(x / S) and floor(x / P) for x < 2^31 as __umulhi(x, m) >> sh with m = ceil(2^(32+sh) / d), 2^(sh+1) >= d
@@ -249,9 +255,7 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   constexpr int SPAN = TILE_N * N + K - N + 4;
   constexpr int SPAN4 = (SPAN + 3) / 4;
   __shared__ __align__(16) float xs[Pad<S>::floats(SPAN4 * 4)];
-  __shared__ int s_bound[POOL ? N : 1][2];                        // per band: start of bin ilo+1, end of bin ilo
-  __shared__ __align__(16) float s_pool[POOL ? N : 1][POOL ? PQ_THREADS : 4];  // per-thread sums of |v|, one row per band
-  __shared__ float s_mix[POOL ? N : 1][PQ_THREADS / 32][2];                    // bin-slot sums of boundary warps
+  __shared__ int s_bound[POOL ? N : 1][3];                        // per band: start of bin ilo+1, end of bin ilo, ilo
 
   const int b = blockIdx.x / tiles_per_row;
   const int tile = blockIdx.x - b * tiles_per_row;
@@ -272,6 +276,7 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
       const unsigned q = magic_div(num, pool.mP, pool.shP);
       s_bound[threadIdx.x][0] = (int)q;
       s_bound[threadIdx.x][1] = (int)(q + (num - q * (unsigned)pool.P != 0u ? 1u : 0u));
+      s_bound[threadIdx.x][2] = (int)ilo;
     }
   }
   __syncthreads();
@@ -416,7 +421,12 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   }
 
   if constexpr (POOL) {
-    constexpr int NW = PQ_THREADS / 32;
+    // Fixed-point pooling: a thread's sum of |v| over its Q steps of one band is rounded to a multiple of 2^-22 (bands
+    // of a normalised clip are bounded by sum|H| < 2, so a warp's 32 sums fit 32 bits), the warp adds them with ONE
+    // redux.sync, and lane 0 adds the warp's total to the 64-bit accumulator of its bin with one red.global.add.u64.
+    // Integer adds commute, so the result does not depend on the order in which warps and CTAs arrive -- bit-identical
+    // from run to run like the shared-memory tree this replaces, with no shared memory, no barrier and no second
+    // phase.  A warp whose 32*Q elements touch the bin boundary (one in ~5) sends two masked sums.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (n_tile + TILE_N > L) {  // last tile of a row (CTA-uniform, rare): steps past the end contribute nothing
       const int nv = L - n0;
@@ -427,21 +437,21 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
           for (int k = 0; k < N; ++k) acc[q][k] = 0.0f;
         }
     }
-    // Per thread and band one value (the sum of its |v|) goes to shared memory; a warp whose 32*Q elements all lie in
-    // one bin (the usual case: bins are ~5 warps wide) is credited to that bin as a whole after the barrier.  Only a
-    // warp that straddles the bin boundary splits its sum itself (shuffle tree) into s_mix.
+    unsigned long long* bins = pool.acc + (size_t)b * pool.P;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       float a[Q];
 #pragma unroll
       for (int q = 0; q < Q; ++q) a[q] = fabsf(acc[q][k]);
-      float t = a[0];
-#pragma unroll
-      for (int q = 1; q < Q; ++q) t += a[q];
-      s_pool[k][threadIdx.x] = t;
-      const int s1 = s_bound[k][0], e0 = s_bound[k][1];
+      const int s1 = s_bound[k][0], e0 = s_bound[k][1], ilo = s_bound[k][2];
       const int wfirst = k * L + n_tile + warp * 32 * Q, wlast = wfirst + 32 * Q - 1;
-      if (!(wlast < s1 || wfirst >= e0)) {  // warp-uniform: this warp straddles the boundary of band k
+      if (wlast < s1 || wfirst >= e0) {  // warp-uniform: the whole warp lies in one bin
+        float t = a[0];
+#pragma unroll
+        for (int q = 1; q < Q; ++q) t += a[q];
+        const unsigned tot = __reduce_add_sync(0xffffffffu, pool_fixed(t));
+        if (lane == 0) atomicAdd(bins + ilo + (wfirst >= e0 ? 1 : 0), (unsigned long long)tot);
+      } else {
         const int f0 = k * L + n0;
         float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
@@ -449,71 +459,26 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
           sum0 += (f0 + q < e0) ? a[q] : 0.0f;
           sum1 += (f0 + q >= s1) ? a[q] : 0.0f;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          sum0 += __shfl_xor_sync(0xffffffffu, sum0, o);
-          sum1 += __shfl_xor_sync(0xffffffffu, sum1, o);
-        }
+        const unsigned t0s = __reduce_add_sync(0xffffffffu, pool_fixed(sum0));
+        const unsigned t1s = __reduce_add_sync(0xffffffffu, pool_fixed(sum1));
         if (lane == 0) {
-          s_mix[k][warp][0] = sum0;
-          s_mix[k][warp][1] = sum1;
+          atomicAdd(bins + ilo, (unsigned long long)t0s);
+          if (ilo + 1 < pool.P) atomicAdd(bins + ilo + 1, (unsigned long long)t1s);
         }
-      }
-    }
-    __syncthreads();
-    // band r: lanes 8w..8w+7 hold the 32 per-thread sums of source warp w (4 each); three shuffle steps give the
-    // per-warp sums, which lane 0 credits to the two bin slots in warp order
-    for (int r = warp; r < N; r += NW) {
-      const float4 v = *reinterpret_cast<const float4*>(&s_pool[r][4 * lane]);
-      float t = (v.x + v.y) + (v.z + v.w);
-      t += __shfl_xor_sync(0xffffffffu, t, 1);
-      t += __shfl_xor_sync(0xffffffffu, t, 2);
-      t += __shfl_xor_sync(0xffffffffu, t, 4);
-      // every lane resolves the bin slots of its own source warp (lane >> 3) in parallel; lane 0 then adds the NW
-      // contributions in warp order
-      static_assert(NW == 4, "8 lanes per source warp");
-      const int sw = lane >> 3;
-      const int s1 = s_bound[r][0], e0 = s_bound[r][1];
-      const int wfirst = r * L + n_tile + sw * 32 * Q, wlast = wfirst + 32 * Q - 1;
-      const bool lo = wlast < s1, hi = wfirst >= e0;
-      float c0 = lo ? t : 0.0f, c1 = hi ? t : 0.0f;
-      if (!lo && !hi) {
-        c0 = s_mix[r][sw][0];
-        c1 = s_mix[r][sw][1];
-      }
-      float slot0 = __shfl_sync(0xffffffffu, c0, 0), slot1 = __shfl_sync(0xffffffffu, c1, 0);
-#pragma unroll
-      for (int w = 1; w < NW; ++w) {
-        slot0 += __shfl_sync(0xffffffffu, c0, 8 * w);
-        slot1 += __shfl_sync(0xffffffffu, c1, 8 * w);
-      }
-      if (lane == 0) {
-        float* dst = pool.partial + (((size_t)b * N + r) * tiles_per_row + tile) * 2;
-        *reinterpret_cast<float2*>(dst) = make_float2(slot0, slot1);
       }
     }
   }
 }
 
-// feat[b][i] = mean of |bands_flat[b][s_i .. e_i)| from the per-CTA partial sums of the pooled analysis epilogue.
-__global__ void k_pool_finalize(const float* __restrict__ partial, float* __restrict__ feat, int B, int N, int L,
-                                int tiles, int tile_n, int P) {
+// feat[b][i] = mean of |bands_flat[b][s_i .. e_i)| from the fixed-point bin accumulators of the pooled analysis epilogue.
+__global__ void k_pool_finalize_fixed(const unsigned long long* __restrict__ acc, float* __restrict__ feat, int B, int N,
+                                      int L, int P) {
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (unsigned)(B * P)) return;
-  // 32-bit arithmetic throughout: N * L * P < 2^31 (checked by the launcher)
-  const unsigned uP = (unsigned)P, uL = (unsigned)L, S = (unsigned)N * uL, tn = (unsigned)tile_n;
-  const unsigned b = idx / uP, i = idx - b * uP;
+  const unsigned uP = (unsigned)P, S = (unsigned)N * (unsigned)L;  // S * P < 2^31 (checked by the launcher)
+  const unsigned i = idx % uP;
   const unsigned s = (i * S) / uP, e = ((i + 1u) * S + uP - 1u) / uP;
-  float sum = 0.0f;
-  const unsigned k0 = s / uL, k1 = (e - 1u) / uL;
-  for (unsigned k = k0; k <= k1; ++k) {
-    const unsigned na = max(s, k * uL) - k * uL, nb = min(e, (k + 1u) * uL) - k * uL;
-    for (unsigned t = na / tn; t <= (nb - 1u) / tn; ++t) {
-      const unsigned slot = i - ((k * uL + t * tn) * uP) / S;
-      if (slot <= 1u) sum += partial[(((size_t)b * N + k) * tiles + t) * 2 + slot];
-    }
-  }
-  feat[idx] = sum / (float)(e - s);
+  feat[idx] = (float)((double)acc[idx] * (1.0 / (double)IAS_POOL_SCALE) / (double)(e - s));
 }
 
 // Any (N, K): one thread per output, taps from global memory.  Correct for shapes without a specialised kernel.
@@ -918,7 +883,10 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
     const size_t need = (size_t)B * N * tiles * 2 * sizeof(float);
     IAS_REQUIRE(pr->workspace && pr->workspace_bytes >= need, IAS_ERR_INVALID,
                 "ias_pqmf_analysis_pooled: workspace %zu < %zu bytes", pr->workspace_bytes, need);
-    pool.partial = static_cast<float*>(pr->workspace);
+    pool.acc = static_cast<unsigned long long*>(pr->workspace);  // B*P*8 <= need: P <= S / (TILE_N + 1)
+    IAS_REQUIRE((reinterpret_cast<uintptr_t>(pr->workspace) & 7u) == 0, IAS_ERR_INVALID,
+                "ias_pqmf_analysis_pooled: workspace must be 8-byte aligned");
+    IAS_CUDA(cudaMemsetAsync(pool.acc, 0, (size_t)B * pr->P * sizeof(unsigned long long), st));
     pool.P = pr->P;
     pool.S = (int)S;
     magic_for((unsigned)S, pool.mS, pool.shS);
@@ -966,7 +934,7 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
   IAS_LAUNCH_CHECK("k_pqmf_analysis");
   if (pr) {
     ProfScope prof2_(K_POOL_FINALIZE, st);
-    k_pool_finalize<<<(B * pr->P + 255) / 256, 256, 0, st>>>(pool.partial, pr->feat, B, N, L, tiles, TILE_N, pr->P);
+    k_pool_finalize_fixed<<<(B * pr->P + 255) / 256, 256, 0, st>>>(pool.acc, pr->feat, B, N, L, pr->P);
     IAS_LAUNCH_CHECK("k_pool_finalize");
   }
   return IAS_OK;
