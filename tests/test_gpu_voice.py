@@ -97,7 +97,7 @@ def test_control_signals(config1):
     assert float((ctrl - ref).abs().max()) <= 2.4e-7
     mism = float((_bits(ctrl) != _bits(ref)).float().mean())
     print(f"control-rate signals: {mism:.4%} of points differ from torch CPU (by <= {float((ctrl-ref).abs().max()):.2e})")
-    assert mism <= 0.02
+    assert mism <= 0.005  # measured 0.25 %: only the LFO cosine (correctly rounded here, MKL VML in torch) differs
 
 
 def test_audio_stage_bit_exact_phases_given_control_signals(config1, cuda_device):
@@ -143,6 +143,7 @@ def test_end_to_end_audio_vs_oracle(config1):
     bad = err > 1e-4
     assert bool(differs[bad].all()), f"voices {torch.nonzero(bad & ~differs).flatten().tolist()} exceed 1e-4 with bit-equal control signals"
     clean = ~differs
+    assert int(clean.sum()) >= 20  # measured 27: another control function drifting by an ulp would empty this set
     print(f"voices with bit-equal control signals: {int(clean.sum())}/128, their max audio error {float(err[clean].max()):.2e}")
     assert float(err[clean].max()) <= 1e-5
     # kernel vs fp64 is no worse than the reference-style fp32 path vs fp64 (per voice, with 1e-4 slack)
