@@ -881,10 +881,12 @@ __global__ void __launch_bounds__(256) k_stats_publish(const float* __restrict__
   }
   if (i4 < n4)
     for (int q = part; q < world; q += PUB_PARTS) *reinterpret_cast<float4*>(peers.base[q] + slot + f) = v;
-  // last CTA done: every CTA's packet stores are ordered before its arrival, the last arrival publishes the flag
-  __threadfence_system();
+  // last CTA done: every CTA's packet stores are ordered before its arrival, the last arrival publishes the flag.
+  // ONE system-scope fence per CTA, by the thread that arrives: the barrier orders the other threads' stores before it
+  // (cumulativity), and a fence per thread -- 99 k MEMBAR.SYS per launch -- was most of this kernel's time at N = 8.
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     int* done = reinterpret_cast<int*>(own + XCHG_DONE);
     if (atomicAdd(done, 1) == (int)gridDim.x - 1) {
       *done = 0;
