@@ -17,7 +17,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,b_local,D", [(2, 256, 256), (4, 1024, 256), (3, 100, 200)])
+@pytest.mark.parametrize("world,b_local,D", [(1, 256, 256), (2, 256, 256), (4, 1024, 256), (3, 100, 200)])
 def test_statistics_exchange_emulated_ranks_on_one_gpu(cuda_device, world, b_local, D):
     proc = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stats_emulate.py"), str(world), str(b_local),
                            str(D)], capture_output=True, text=True, timeout=600)
