@@ -178,7 +178,24 @@ k_voice_adsr(const float* __restrict__ params01, int B, int C, float cr, float e
     s_v[tid] = from_0to1(params01[(size_t)row * B + b], ranges.r[row]);
   }
   __syncthreads();
-  if (tid < 3) adsr_setup_part(s_adsr, tid, s_v, s_v[5], cr, eps, C);
+  if (tid < 3) {
+    // the three ramps of the envelope on three lanes of ONE warp running the SAME code (duration / start / direction
+    // chosen with selects): ramp_setup -- two SLEEF pows and the saturation search, ~800 instructions -- executes
+    // once for the three lanes instead of three times in a row, as it did behind adsr_setup_part's if / else chain
+    const float note_on = s_v[5], alpha = s_v[4];
+    const float new_attack = fminf(s_v[0], note_on);
+    const float new_decay = fminf(fmaxf(sub(note_on, s_v[0]), 0.0f), s_v[1]);
+    const float dur = mul(tid == 0 ? new_attack : (tid == 1 ? new_decay : s_v[3]), cr);
+    const float start = tid == 0 ? 0.0f : mul(tid == 1 ? new_attack : note_on, cr);
+    const Ramp r = ramp_setup(dur, start, tid != 0, alpha, eps, C);
+    Ramp* dst = tid == 0 ? &s_adsr.a : (tid == 1 ? &s_adsr.d : &s_adsr.r);
+    *dst = r;
+    if (tid == 0) {
+      s_adsr.sustain = s_v[2];
+      s_adsr.one_minus_sustain = sub(1.0f, s_v[2]);
+      s_adsr.alpha = alpha;
+    }
+  }
   __syncthreads();
   float* out = env + ((size_t)b * 6 + e) * C;
   for (int j = tid; j < C; j += ADSR_THREADS) out[j] = adsr_eval(s_adsr, (float)j, eps);
