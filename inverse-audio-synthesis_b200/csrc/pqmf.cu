@@ -24,6 +24,38 @@ namespace {
 
 constexpr int PQ_THREADS = 128;
 
+// ---- TMA bulk copy (cp.async.bulk, 1-D) + mbarrier: stages a linear signal tile with ONE instruction of one thread
+#ifndef IAS_PQMF_BULK
+#define IAS_PQMF_BULK 1
+#endif
+__device__ __forceinline__ uint32_t pq_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pq_bulk_stage(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  const uint32_t b = pq_smem_u32(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   pq_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(b)
+               : "memory");
+}
+// Bounded wait on phase 0: a lost completion traps instead of hanging the GPU.
+__device__ __forceinline__ void pq_bulk_wait(uint64_t* bar) {
+  const uint32_t b = pq_smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(b)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
 template <int N, int K>
 struct Taps {
   float h[N * K];
@@ -263,11 +295,21 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   const float scale = row_scale ? row_scale[b] : 1.0f;
   const int g0 = n_tile * N - PAD - OFF;  // multiple of 4
   const bool vec_ok = ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
-  // the per-row gain is applied to the accumulators (linear), so the staged samples are the raw input
-  if (vec_ok && g0 >= 0 && g0 + 4 * SPAN4 <= T)
+  // the per-row gain is applied to the accumulators (linear), so the staged samples are the raw input.
+  // Interior tiles whose shared-memory layout is linear (chunk pitch == chunk size: N = 3) arrive by ONE bulk copy
+  // (cp.async.bulk, the TMA engine) issued by thread 0 and tracked by an mbarrier -- no LDG / STS instructions, no
+  // shared-memory store wavefronts; other layouts and the first / last tile of a row take the register path.
+  constexpr bool LINEAR = Pad<S>::VEC && Pad<S>::SP == S && IAS_PQMF_BULK;
+  __shared__ __align__(8) uint64_t s_bar;
+  const bool interior = vec_ok && g0 >= 0 && g0 + 4 * SPAN4 <= T;  // CTA-uniform
+  const bool bulk = LINEAR && interior;
+  if (bulk) {
+    if (threadIdx.x == 0) pq_bulk_stage(xs, x + (size_t)b * T + g0, SPAN4 * 16, &s_bar);
+  } else if (interior) {
     stage_row_interior<S, SPAN4>(xs, x + (size_t)b * T + g0);
-  else
+  } else {
     stage_row<S, SPAN4>(xs, x + (size_t)b * T, g0, T, 1.0f, vec_ok);
+  }
   if constexpr (POOL) {
     if (threadIdx.x < N) {  // 32-bit arithmetic: S * P < 2^31 (checked by the launcher)
       const unsigned first = (unsigned)((int)threadIdx.x * L + n_tile);
@@ -279,7 +321,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
       s_bound[threadIdx.x][2] = (int)ilo;
     }
   }
-  __syncthreads();
+  __syncthreads();  // staged tile (register path), bin bounds and the mbarrier's initialisation are visible
+  if (bulk) pq_bulk_wait(&s_bar);
 
   float acc[Q][N];
 #pragma unroll

@@ -18,7 +18,7 @@ LIB = os.path.join(ROOT, "inverse-audio-synthesis_b200", "ias_b200", "libias_b20
 PROF = os.path.join(ROOT, "profiles")
 TC = re.compile(r"UTCHMMA|UTCQMMA|UTCMMA|LDTM|STTM|UBLKCP|UTCBAR|UTCATOMSWS|SYNCS|UTMALDG|FENCE\.VIEW")
 TARGETS = {"k_gram_tc": TC, "k_bwd_tc": TC, "k_voice_audioILi128ELi16ELi4ELb1ELb0": re.compile(r"FFMA2|FADD2|FMUL2|DADD|F2F|MUFU"),
-           "k_pqmf_analysisILi3ELi63ELi4ENS0_6TapsCMILi3ELi63EEELb1": re.compile(r"FFMA2|LDS|STG|LDCU")}
+           "k_pqmf_analysisILi3ELi63ELi4ENS0_6TapsCMILi3ELi63EEELb1": re.compile(r"UBLKCP|SYNCS|FFMA2|LDS|STG|LDCU|REDUX|REDG")}
 
 
 def main():
