@@ -24,13 +24,15 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--seconds", type=float, default=4.0)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--no-normalize", action="store_true", help="Voice(normalize=False): skip normalize_if_clipping")
+    ap.add_argument("--non-reproducible", action="store_true", help="[B,T] noise table from HBM")
     ap.add_argument("shapes", nargs="*", default=["128x8x7", "128x8x6", "128x16x4", "128x16x3", "256x8x3", "256x16x2"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     lib = ias_b200.lib()
-    cfg = ias_b200.SynthConfig(batch_size=args.batch, reproducible=True, sample_rate=44100,
+    cfg = ias_b200.SynthConfig(batch_size=args.batch, reproducible=not args.non_reproducible, sample_rate=44100,
                                buffer_size_seconds=args.seconds)
-    voice = ias_b200.Voice(synthconfig=cfg).to(dev)
+    voice = ias_b200.Voice(synthconfig=cfg, normalize=not args.no_normalize).to(dev)
     voice.randomize(seed=7)
     ref = None
     for shape in args.shapes:
