@@ -63,6 +63,13 @@ def parse():
                          "noise table (722 MB at 1024 x 4 s) that the render streams from HBM every step")
     ap.add_argument("--no-nonreproducible", "--no-noise-variant", dest="no_noise_variant", action="store_true",
                     help="skip the e2e variant with the other noise mode")
+    ap.add_argument("--normalize", default="defer", choices=["defer", "kernel"],
+                    help="normalize_if_clipping of the rendered audio: defer = Voice(normalize='defer'): the render leaves "
+                         "the raw mix and a [B] factor (1/peak of a clipping row, else 1) that PQMF.analysis applies to the "
+                         "bands it writes (the filter bank is linear), so the clipping rows (13 %% of the voices) are not "
+                         "read and written a second time; kernel = Voice(normalize=True): the audio tensor itself is "
+                         "normalised by a second pass inside the render (what Voice.forward returns to a caller that wants "
+                         "the audio)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (outside the timed region)")
     ap.add_argument("--parity-sounds", type=int, default=0,
                     help="sounds of the parity block's CPU oracle render (default: 128 at 4 s, 16 for long clips)")
@@ -297,7 +304,7 @@ def parity_block(args, rank, world, dev, voice, gram, vic, wa, wp):
     # ---- exchange route: N ranks == oracle on the concatenation ----
     batch_no = 900_001
     audio, params, _ = voice(batch_no * world + rank)
-    _, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
+    _, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice.row_scale)
     with torch.no_grad():
         l4 = torch.stack(vic.loss(x, y)).double()
     xy = torch.cat([x, y], dim=1).contiguous()
@@ -332,19 +339,22 @@ def parity_block(args, rank, world, dev, voice, gram, vic, wa, wp):
                                        reproducible=args.reproducible)
         cfgP = ias_b200.SynthConfig(batch_size=Bv, reproducible=args.reproducible, sample_rate=44100,
                                     buffer_size_seconds=args.seconds)
-        vP = ias_b200.Voice(synthconfig=cfgP).to(dev)
+        vP = ias_b200.Voice(synthconfig=cfgP, normalize=voice.normalize).to(dev)
         vcfg = types.SimpleNamespace(dim=D, embeddim=D, vicreg=types.SimpleNamespace(
             mlp="8-8-%d", batch_size=P, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
         vicP = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity(), gather=False)
         a, prm, _ = vP(0)
         a, prm = a[:P].contiguous(), prm[:P].contiguous()
-        err = (a.cpu() - ref["audio"]).abs().max(dim=1)[0]
+        scaleP = vP.row_scale[:P].contiguous() if vP.row_scale is not None else None
+        # deferred normalisation: the audio tensor is the raw mix; what is compared is raw * factor
+        a_cmp = a if scaleP is None else a * scaleP[:, None]
+        err = (a_cmp.cpu() - ref["audio"]).abs().max(dim=1)[0]
         bands_ref_in = gram(ref["audio"].unsqueeze(1).to(dev)).cpu()
         pq = float((bands_ref_in - ref["bands"]).abs().max() / ref["bands"].abs().max())
         want = np.array(ref["loss4"])
         with torch.no_grad():
             g_or = np.array([float(v) for v in vicP.loss(ref["x"].to(dev), ref["y"].to(dev))])
-            _, xg, yg = harness.analysis_bridge(gram, a, prm, wa, wp)
+            _, xg, yg = harness.analysis_bridge(gram, a, prm, wa, wp, scaleP)
             g_e2e = np.array([float(v) for v in vicP.loss(xg, yg)])
         rel_or = np.abs(g_or - want) / np.abs(want)
         rel_e2e = np.abs(g_e2e - want) / np.abs(want)
@@ -396,7 +406,7 @@ def run_ours(args):
     T = int(args.seconds * 44100)
     cfg = ias_b200.SynthConfig(batch_size=B, reproducible=args.reproducible, sample_rate=44100,
                                buffer_size_seconds=args.seconds)
-    voice = ias_b200.Voice(synthconfig=cfg).to(dev)
+    voice = ias_b200.Voice(synthconfig=cfg, normalize="defer" if args.normalize == "defer" else True).to(dev)
     gram = ias_b200.PQMF(N=args.bands).to(dev)
     vcfg = types.SimpleNamespace(dim=D, embeddim=D, vicreg=types.SimpleNamespace(
         mlp="8-8-%d", batch_size=B * world, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
@@ -418,7 +428,7 @@ def run_ours(args):
 
     def step(i: int):
         audio, params, _ = voice(i * world + rank)       # sound ids [ (i*W + r) * B, ... ): SURVEY 8(d) config 4
-        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
+        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice.row_scale)
         with torch.no_grad():
             return vic.loss(x, y)
 
@@ -435,7 +445,7 @@ def run_ours(args):
 
     def step_index(idx):
         audio, params, _ = voice(idx)                    # a device-resident index is read by the seeding kernel
-        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
+        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice.row_scale)
         with torch.no_grad():
             return vic.loss(x, y)
 
@@ -465,7 +475,7 @@ def run_ours(args):
             else:
                 idx_dev.add_(world)
             voice.prepare(idx_dev)
-        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
+        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice.row_scale)
         with torch.no_grad():
             out = torch.stack(vic.loss(x, y))
         if result_to_host is not None:
@@ -628,7 +638,7 @@ def run_ours(args):
     def step_host_params():
         voice._store.copy_(host_params, non_blocking=True)
         audio = voice.output()
-        bands, x, y = harness.analysis_bridge(gram, audio, voice.params01(), wa, wp)
+        bands, x, y = harness.analysis_bridge(gram, audio, voice.params01(), wa, wp, voice.row_scale)
         with torch.no_grad():
             o = vic.loss(x, y)
         host_out.copy_(torch.stack(o))
@@ -651,12 +661,12 @@ def run_ours(args):
     if not args.no_noise_variant:
         cfg_nr = ias_b200.SynthConfig(batch_size=B, reproducible=not args.reproducible, sample_rate=44100,
                                       buffer_size_seconds=args.seconds)
-        voice_nr = ias_b200.Voice(synthconfig=cfg_nr).to(dev)
+        voice_nr = ias_b200.Voice(synthconfig=cfg_nr, normalize=voice.normalize).to(dev)
 
         def step_e2e_nr():
             idx_dev.copy_(host_in, non_blocking=True)
             audio, params, _ = voice_nr(idx_dev)
-            bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp)
+            bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice_nr.row_scale)
             with torch.no_grad():
                 out = torch.stack(vic.loss(x, y))
             host_out.copy_(out, non_blocking=True)
@@ -786,6 +796,11 @@ def run_ours(args):
                       "reproducible=False, the reference's setting (conf/config.yaml:38): [B,T] noise table, %.0f MB "
                       "streamed from HBM every step" % (4e-6 * B * T)) + "; the other mode is timed beside it as "
                                                                             "e2e_noise_variant",
+            "normalize": ("deferred: the render leaves the raw mix + a [B] factor (1/peak of a clipping row, else 1), the "
+                          "PQMF analysis applies it to the bands it writes (Voice(normalize='defer'), "
+                          "PQMF.analysis(row_scale=)); bands / loss as with the in-render pass to rounding, checked by the "
+                          "parity block" if args.normalize == "defer" else
+                          "in the render (Voice(normalize=True)): second pass over the clipping rows"),
             "l2": "inputs larger than L2: %.0f MB audio + %.0f MB bands per step vs 126 MB L2" % (
                 4e-6 * B * T, 4e-6 * B * T),
             "bridge": "abs-mean pool to 256 bins + 2 torch matmuls (harness, not a reference component), inside the "

@@ -51,21 +51,23 @@ def bridge(bands: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torc
     return feat @ wa, params @ wp
 
 
-def analysis_bridge(gram, audio: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torch.Tensor):
+def analysis_bridge(gram, audio: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torch.Tensor,
+                    row_scale: torch.Tensor | None = None):
     """Device path of ``bridge(gram(audio), params)`` with the pooling fused into the PQMF analysis kernel
-    (``PQMF.analysis_pooled``): the bands make one trip to HBM.  -> (bands, x, y)."""
+    (``PQMF.analysis_pooled``): the bands make one trip to HBM.  ``row_scale`` = ``Voice(normalize="defer").row_scale``
+    folds normalize_if_clipping into the analysis (the filter bank is linear).  -> (bands, x, y)."""
     from ias_b200 import IasError, _lib
 
     global LAST_BRIDGE_PATH
     x3 = audio.unsqueeze(1) if audio.dim() == 2 else audio
     try:
-        bands, feat = gram.analysis_pooled(x3, EMBED_DIM)
+        bands, feat = gram.analysis_pooled(x3, EMBED_DIM, row_scale=row_scale)
     except IasError as exc:
         # only "this shape has no fused kernel" (bins narrower than a CTA tile: short clips) may take the unfused
         # device kernels; a launch failure, a workspace error or a missing library must surface
         if exc.code != _lib.IAS_ERR_UNSUPPORTED:
             raise
-        bands = gram(x3)
+        bands = gram.analysis(x3, row_scale=row_scale)
         x, y = bridge(bands, params, wa, wp)
         LAST_BRIDGE_PATH = "unfused: ias_pqmf_analysis + ias_abs_avg_pool"
         return bands, x, y

@@ -88,9 +88,11 @@ IAS_API int ias_voice_control(const float* params01, int B, int C, float control
                       void* workspace, size_t workspace_bytes, ias_stream_t stream);
 
 /* Voice.output(): params -> audio[B][T].  noise[noise_rows][T] is the Noise module buffer (row b uses
- * noise[b % noise_rows]).  peak[B] receives max|mixed| before normalisation (may be NULL).  normalize != 0 applies
- * util.normalize_if_clipping (x / peak where peak > 1); normalize == 0 leaves the raw mix so a consumer can fold
- * the scale in.  Two inspection hooks for the parity tests, both normally NULL: ctrl_in[B][5][C] replaces the
+ * noise[b % noise_rows]).  peak[B] receives max|mixed| before normalisation (may be NULL).  normalize == 1 applies
+ * util.normalize_if_clipping (x / peak where peak > 1) -- a second pass over the clipping rows; normalize == 0 leaves
+ * the raw mix; normalize == 2 defers the normalisation to the consumer: audio is the raw mix and peak[B] receives the
+ * factor to apply instead (RN(1/peak) for a clipping row, else 1) -- exactly the row_scale argument of
+ * ias_pqmf_analysis*, so synth -> PQMF needs no second pass over the audio.  Two inspection hooks for the parity tests, both normally NULL: ctrl_in[B][5][C] replaces the
  * control-rate signals the audio stage reads (the per-voice constants still come from params01), and phase_dbg
  * receives the two VCO cosine arguments, [B][2][T]. */
 IAS_API int ias_voice_render(const float* params01, const float* noise, int noise_rows, float* audio, float* peak, int B,

@@ -467,7 +467,8 @@ struct AudioArgs {
   int B, T, C, noise_rows;
   float scale;          // float(C-1)/float(T-1)
   float sr, rsr;
-  int normalize;
+  int normalize;  // 0: none; 1: normalize_if_clipping in the kernel; 2: deferred -- audio stays un-normalised and
+                  // peak[b] receives the factor the consumer applies (1/peak of a clipping row, else 1)
 };
 
 // ---- packed fp32 (sm_100: FFMA2 / FADD2 / FMUL2 process two fp32 lanes per instruction) --------------------------
@@ -891,8 +892,8 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
     float pkv = s_peak[0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) pkv = fmaxf(pkv, s_peak[w]);
-    if (tid == 0 && A.peak) A.peak[b] = pkv;
-    if (A.normalize && pkv > 1.0f) {
+    if (tid == 0 && A.peak) A.peak[b] = A.normalize == 2 ? (pkv > 1.0f ? vm::div(1.0f, pkv) : 1.0f) : pkv;
+    if (A.normalize == 1 && pkv > 1.0f) {
       // x / peak, correctly rounded (Markstein step with r = RN(1/peak)); 4 independent 16-byte loads in flight per
       // thread so this second pass over the row runs at memory speed instead of one round trip per iteration
       const float rp = vm::div(1.0f, pkv);
@@ -923,6 +924,306 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
       }
     }
     // the barrier above separates this iteration's read of s_slot from the next iteration's write
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_voice_audio_sp: the same arithmetic, software-pipelined across tiles
+// ------------------------------------------------------------------------------------------------------------
+// ncu of k_voice_audio (profiles/r2y): a warp spends 21 % of its time in pass 1 (FMA pipe only), 45 % in pass 2 (which
+// needs 768 XU-pipe cycles per tile for 512 FMA-pipe cycles and is a chain of F2F -> reduction -> MUFU -> ... with
+// little to issue while a result is in flight) and 20 % in the scan / barrier; with four warps per scheduler the two
+// pipes are busy one after the other rather than together (FMA 5270 + XU 4096 cycles per round of four tiles, 9600
+// measured).  Here pass 2 of tile t and pass 1 of tile t+1 are ONE straight-line block per thread: for every sample
+// pair the oscillators of tile t are evaluated and the pitch chains of tile t+1 overwrite the increments just consumed
+// (x1, x2, srcs are recycled in place), so the scheduler always has FMA-only chains to issue under the XU latencies.
+// The increments stay fp32 in registers between the passes and are widened to fp64 where they are added (the
+// classic kernel keeps 32 converted doubles = 64 registers alive across the barrier); the widening is two integer
+// instructions instead of an XU-pipe F2F (increments are positive normal numbers).  Same operations on the same
+// operands in the same order per sample: audio is bit-identical to k_voice_audio (tests/test_gpu_voice.py).
+#ifndef IAS_SP_F2D_BITS
+#define IAS_SP_F2D_BITS 1
+#endif
+#ifndef IAS_SP_PITCH_FIRST  // 1: source order pitch chain (t+1) before oscillators (t) within a sample pair
+#define IAS_SP_PITCH_FIRST 0
+#endif
+#ifndef IAS_SP_RECOMPUTE_SRC  // 1: pass 2 recomputes the source coordinates instead of keeping 16 registers
+#define IAS_SP_RECOMPUTE_SRC 0
+#endif
+__device__ __forceinline__ double widen_pos(float x) {
+#if IAS_SP_F2D_BITS
+  // fp32 -> fp64 of a positive normal number, exact: exponent re-biased (+896), mantissa moved up 29 bits
+  const unsigned b = (unsigned)f2i(x);
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+#else
+  return (double)x;
+#endif
+}
+
+// pitch chain of the sample pair (k, k+1) of the tile whose first sample of this thread is ft0 (interval fj)
+template <bool CLAMP>
+__device__ __forceinline__ void pitch_pair(int k, float ft0, float scale, float fj, float fj1, const float4 r0,
+                                           const float4 r1, float midi1, float depth1, float midi2, float depth2,
+                                           float sr, float rsr, P2& i1, P2& i2, P2& sp) {
+  const P2 fi = p2_add(p2b(ft0), p2((float)k, (float)(k + 1)));
+  sp = p2_fma(p2b(scale), fi, p2b(0.0f));
+  const float s0 = p2lo(sp), s1 = p2hi(sp);
+  const bool d0 = s0 >= fj1, d1 = s1 >= fj1;
+  const P2 l1 = p2_sub(sp, p2(d0 ? fj1 : fj, d1 ? fj1 : fj));
+  const P2 l0 = p2_sub(p2b(1.0f), l1);
+  const P2 m1 = p2_fma(l0, p2(d0 ? r0.y : r0.x, d1 ? r0.y : r0.x), p2_mul(l1, p2(d0 ? r0.z : r0.y, d1 ? r0.z : r0.y)));
+  const P2 m2 = p2_fma(l0, p2(d0 ? r1.x : r0.w, d1 ? r1.x : r0.w), p2_mul(l1, p2(d0 ? r1.y : r1.x, d1 ? r1.y : r1.x)));
+  i1 = vco_increment_p2<CLAMP>(midi1, depth1, m1, sr, rsr);
+  i2 = vco_increment_p2<CLAMP>(midi2, depth2, m2, sr, rsr);
+}
+
+struct SpVoice {  // per-voice constants of the merged block
+  float midi1, depth1, phase1, midi2, depth2, phase2, pk, shape, scale, sr, rsr;
+};
+
+// pass 2 of the current tile + pass 1 of the next one, one straight-line block
+template <int SPT, bool CLAMP, bool DBG>
+__device__ __forceinline__ void merged_passes(float (&x1)[SPT], float (&x2)[SPT], float (&srcs)[SPT], float (&y)[SPT],
+                                              const float (&nzv)[SPT], double& acc1, double& acc2, double& tot1,
+                                              double& tot2, float& lpeak, const SpVoice& V, float ft0, float fj,
+                                              float fj1, const float4 r1, const float4 r2, const float4 r3, float ft0n,
+                                              float fjn, float fj1n, const float4 r0n, const float4 r1n,
+                                              float* dbg1, float* dbg2, int t0, int T) {
+#pragma unroll
+  for (int k = 0; k < SPT; k += 2) {
+#if IAS_SP_PITCH_FIRST
+    P2 i1, i2, spn;
+    pitch_pair<CLAMP>(k, ft0n, V.scale, fjn, fj1n, r0n, r1n, V.midi1, V.depth1, V.midi2, V.depth2, V.sr, V.rsr, i1, i2,
+                      spn);
+#endif
+    // ---- tile t, pass 2 ----
+#if IAS_SP_RECOMPUTE_SRC
+    const P2 sp = p2_fma(p2b(V.scale), p2_add(p2b(ft0), p2((float)k, (float)(k + 1))), p2b(0.0f));
+#else
+    const P2 sp = p2(srcs[k], srcs[k + 1]);
+#endif
+    const P2 u = p2_sub(sp, p2b(fj));
+    const P2 um = p2_sub(sp, p2b(fj1));
+    const P2 r = p2(fmaxf(p2lo(um), 0.0f), fmaxf(p2hi(um), 0.0f));
+    acc1 += widen_pos(x1[k]);
+    const float a10 = (float)acc1;
+    acc1 += widen_pos(x1[k + 1]);
+    const float a11 = (float)acc1;
+    acc2 += widen_pos(x2[k]);
+    const float a20 = (float)acc2;
+    acc2 += widen_pos(x2[k + 1]);
+    const float a21 = (float)acc2;
+    const P2 arg1 = p2_add(p2(a10, a11), p2b(V.phase1));
+    const P2 arg2 = p2_add(p2(a20, a21), p2b(V.phase2));
+    const P2 g1 = p2_fma(r, p2b(r2.x), p2_fma(u, p2b(r1.w), p2b(r1.z)));
+    const P2 g2 = p2_fma(r, p2b(r2.w), p2_fma(u, p2b(r2.z), p2b(r2.y)));
+    const P2 g3 = p2_fma(r, p2b(r3.z), p2_fma(u, p2b(r3.y), p2b(r3.x)));
+    const P2 yy = p2_fma(cos_arg_p2(arg1), g1,
+                         p2_fma(squaresaw_core_p2(arg2, V.pk, V.shape), g2, p2_mul(p2(nzv[k], nzv[k + 1]), g3)));
+    y[k] = p2lo(yy);
+    y[k + 1] = p2hi(yy);
+    lpeak = fmaxf(lpeak, fmaxf(fabsf(y[k]), fabsf(y[k + 1])));
+    if (DBG) {
+      if ((t0 + k) < T) {
+        dbg1[t0 + k] = p2lo(arg1);
+        dbg2[t0 + k] = p2lo(arg2);
+      }
+      if ((t0 + k + 1) < T) {
+        dbg1[t0 + k + 1] = p2hi(arg1);
+        dbg2[t0 + k + 1] = p2hi(arg2);
+      }
+    }
+    // ---- tile t+1, pass 1: overwrites the increments consumed above ----
+#if !IAS_SP_PITCH_FIRST
+    P2 i1, i2, spn;
+    pitch_pair<CLAMP>(k, ft0n, V.scale, fjn, fj1n, r0n, r1n, V.midi1, V.depth1, V.midi2, V.depth2, V.sr, V.rsr, i1, i2,
+                      spn);
+#endif
+    x1[k] = p2lo(i1);
+    x1[k + 1] = p2hi(i1);
+    x2[k] = p2lo(i2);
+    x2[k + 1] = p2hi(i2);
+#if !IAS_SP_RECOMPUTE_SRC
+    srcs[k] = p2lo(spn);
+    srcs[k + 1] = p2hi(spn);
+#endif
+    tot1 += widen_pos(x1[k]);
+    tot1 += widen_pos(x1[k + 1]);
+    tot2 += widen_pos(x2[k]);
+    tot2 += widen_pos(x2[k + 1]);
+  }
+}
+
+// Requires T % SPT == 0 and 16-byte aligned rows (the VEC case of k_voice_audio; other calls take k_voice_audio).
+template <int NT, int SPT, int MINB, bool DBG>
+__global__ void __launch_bounds__(NT, MINB) k_voice_audio_sp(AudioArgs A) {
+  constexpr int TILE = NT * SPT;
+  constexpr int NW = NT / 32;
+  __shared__ double s_wsum[2][2][NW];  // [buffer][vco][warp]
+  __shared__ float s_peak[NW];
+  __shared__ int s_slot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = A.T, C = A.C;
+  SpVoice V;
+  V.scale = A.scale;
+  V.sr = A.sr;
+  V.rsr = A.rsr;
+  const float fTm1 = (float)(T - 1);
+
+  for (;;) {
+    if (tid == 0) s_slot = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot >= A.B) break;
+    const int b = A.order[slot];
+    const float* vc = A.vconst + (size_t)b * VC_COUNT;
+    V.midi1 = vc[VC_MIDI1]; V.depth1 = vc[VC_DEPTH1]; V.phase1 = vc[VC_PHASE1];
+    V.midi2 = vc[VC_MIDI2]; V.depth2 = vc[VC_DEPTH2]; V.phase2 = vc[VC_PHASE2];
+    V.pk = vc[VC_PK]; V.shape = vc[VC_SHAPE];
+    const bool noclamp = vc[VC_NOCLAMP] != 0.0f;
+    const float4* rec = A.rec + (size_t)b * C * (REC_FLOATS / 4);
+    const float* nz = A.noise + (size_t)(b % A.noise_rows) * T;
+    float* out = A.audio + (size_t)b * T;
+    float* dbg1 = DBG ? A.phase_dbg + ((size_t)b * 2 + 0) * T : nullptr;
+    float* dbg2 = DBG ? A.phase_dbg + ((size_t)b * 2 + 1) * T : nullptr;
+    const int ntiles = A.ntiles[b];
+
+    double carry1 = 0, carry2 = 0;
+    float tpeak = 0.0f;
+    // ---- prologue: pass 1 of tile 0 ----
+    float ft0 = (float)(tid * SPT);
+    int j = min((int)mul(V.scale, fminf(ft0, fTm1)), C - 1);
+    float fj = (float)j, fj1 = add(fj, 1.0f);
+    const float4* rj = rec + (size_t)j * 4;
+    float x1[SPT], x2[SPT], srcs[SPT];
+    double tot1 = 0, tot2 = 0;
+    float4 r1;
+    if (ntiles > 0) {
+      const float4 r0 = __ldg(rj + 0);
+      r1 = __ldg(rj + 1);
+#pragma unroll
+      for (int k = 0; k < SPT; k += 2) {
+        P2 i1, i2, sp;
+        if (noclamp)
+          pitch_pair<false>(k, ft0, V.scale, fj, fj1, r0, r1, V.midi1, V.depth1, V.midi2, V.depth2, V.sr, V.rsr, i1, i2, sp);
+        else
+          pitch_pair<true>(k, ft0, V.scale, fj, fj1, r0, r1, V.midi1, V.depth1, V.midi2, V.depth2, V.sr, V.rsr, i1, i2, sp);
+        x1[k] = p2lo(i1); x1[k + 1] = p2hi(i1);
+        x2[k] = p2lo(i2); x2[k + 1] = p2hi(i2);
+        srcs[k] = p2lo(sp); srcs[k + 1] = p2hi(sp);
+        tot1 += widen_pos(x1[k]);
+        tot1 += widen_pos(x1[k + 1]);
+        tot2 += widen_pos(x2[k]);
+        tot2 += widen_pos(x2[k + 1]);
+      }
+    }
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int t0 = tile * TILE + tid * SPT;
+      const int buf = tile & 1;
+      // ---- block scan of tile t ----
+      const double inc1 = warp_incl_scan(tot1, lane);
+      const double inc2 = warp_incl_scan(tot2, lane);
+      if (lane == 31) {
+        s_wsum[buf][0][warp] = inc1;
+        s_wsum[buf][1][warp] = inc2;
+      }
+      // gains and noise of tile t, pitch points of tile t+1: issued before the barrier
+      const float4 r2 = __ldg(rj + 2);
+      const float4 r3 = __ldg(rj + 3);
+      float nzv[SPT];
+      if (t0 < T) {
+#pragma unroll
+        for (int q = 0; q < SPT / 4; ++q) {
+          const float4 n4 = __ldg(reinterpret_cast<const float4*>(nz + t0) + q);
+          nzv[4 * q + 0] = n4.x; nzv[4 * q + 1] = n4.y; nzv[4 * q + 2] = n4.z; nzv[4 * q + 3] = n4.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < SPT; ++k) nzv[k] = 0.0f;
+      }
+      const float ft0n = add(ft0, (float)TILE);
+      const int jn = min((int)mul(V.scale, fminf(ft0n, fTm1)), C - 1);
+      const float fjn = (float)jn, fj1n = add(fjn, 1.0f);
+      const float4* rjn = rec + (size_t)jn * 4;
+      const float4 r0n = __ldg(rjn + 0);
+      const float4 r1n = __ldg(rjn + 1);
+      if (tile + 2 < ntiles) {  // L1 prefetch two tiles ahead (record) / one ahead (noise)
+        const int jnn = min((int)mul(V.scale, fminf(add(ft0n, (float)TILE), fTm1)), C - 1);
+        prefetch_l1(rec + (size_t)jnn * 4);
+      }
+      if (t0 + TILE < T) prefetch_l1(nz + t0 + TILE);
+      __syncthreads();
+      double acc1 = carry1 + (inc1 - tot1), acc2 = carry2 + (inc2 - tot2);
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const double w1 = s_wsum[buf][0][w], w2 = s_wsum[buf][1][w];
+        if (w < warp) {
+          acc1 += w1;
+          acc2 += w2;
+        }
+        carry1 += w1;
+        carry2 += w2;
+      }
+      // ---- pass 2 of tile t merged with pass 1 of tile t+1 ----
+      float y[SPT];
+      float lpeak = 0.0f;
+      tot1 = 0;
+      tot2 = 0;
+      if (noclamp)
+        merged_passes<SPT, false, DBG>(x1, x2, srcs, y, nzv, acc1, acc2, tot1, tot2, lpeak, V, ft0, fj, fj1, r1, r2, r3,
+                                       ft0n, fjn, fj1n, r0n, r1n, dbg1, dbg2, t0, T);
+      else
+        merged_passes<SPT, true, DBG>(x1, x2, srcs, y, nzv, acc1, acc2, tot1, tot2, lpeak, V, ft0, fj, fj1, r1, r2, r3,
+                                      ft0n, fjn, fj1n, r0n, r1n, dbg1, dbg2, t0, T);
+      // a thread is wholly live or wholly past the end of the clip (T % SPT == 0); threads past the end still ran both
+      // passes: their samples do not exist in the reference and must not reach max|mixed|
+      if (t0 < T) {
+        tpeak = fmaxf(tpeak, lpeak);
+#pragma unroll
+        for (int q = 0; q < SPT / 4; ++q)
+          reinterpret_cast<float4*>(out + t0)[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      }
+      ft0 = ft0n; fj = fjn; fj1 = fj1n; rj = rjn; r1 = r1n;
+    }
+
+    // ---- silent tail ----
+    if ((long long)ntiles * TILE < T) {
+      float4* o4 = reinterpret_cast<float4*>(out);
+      for (int i = ntiles * (TILE / 4) + tid; i < T / 4; i += NT) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // ---- per-voice peak, normalize_if_clipping (as in k_voice_audio) ----
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) tpeak = fmaxf(tpeak, __shfl_xor_sync(0xffffffffu, tpeak, d));
+    if (lane == 0) s_peak[warp] = tpeak;
+    __syncthreads();  // also orders this CTA's global stores before the re-read below
+    float pkv = s_peak[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) pkv = fmaxf(pkv, s_peak[w]);
+    if (tid == 0 && A.peak) A.peak[b] = A.normalize == 2 ? (pkv > 1.0f ? vm::div(1.0f, pkv) : 1.0f) : pkv;
+    if (A.normalize == 1 && pkv > 1.0f) {
+      const float rp = vm::div(1.0f, pkv);
+      const int live = min(T, ntiles * TILE);
+      float4* o4 = reinterpret_cast<float4*>(out);
+      const int n4 = live / 4;
+      constexpr int U = 4;
+      for (int base = 0; base < n4; base += U * NT) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * NT + tid;
+          if (i < n4) v[u] = o4[i];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * NT + tid;
+          if (i < n4) {
+            v[u].x = div_const(v[u].x, pkv, rp); v[u].y = div_const(v[u].y, pkv, rp);
+            v[u].z = div_const(v[u].z, pkv, rp); v[u].w = div_const(v[u].w, pkv, rp);
+            o4[i] = v[u];
+          }
+        }
+      }
+    }
   }
 }
 
@@ -988,14 +1289,21 @@ int sm_count() {
   return v;
 }
 
+// persistent grid of the audio kernels; IAS_VOICE_GRID_PER_SM=<n> (tuning runs) launches fewer CTAs than fit
+int audio_grid(int B, int minb) {
+  static const int env = getenv("IAS_VOICE_GRID_PER_SM") ? atoi(getenv("IAS_VOICE_GRID_PER_SM")) : 0;
+  return std::min(B, sm_count() * ((env > 0 && env < minb) ? env : minb));
+}
+
 // Shape of the audio kernel: threads per CTA, samples per thread per tile, resident CTAs per SM.
 struct AudioShape {
   int nt, spt, ctas_per_sm;
+  int sp;  // 0 classic, 1 software-pipelined (k_voice_audio_sp: needs the 128-bit path, otherwise the classic kernel runs)
 };
 
 template <int NT, int SPT, int MINB>
 int launch_audio_shape(const AudioArgs& a, bool vec, bool dbg, cudaStream_t st) {
-  const int grid = std::min(a.B, sm_count() * MINB);
+  const int grid = audio_grid(a.B, MINB);
   ProfScope prof_(K_VOICE_AUDIO, st);
   if (vec && !dbg)
     k_voice_audio<NT, SPT, MINB, true, false><<<grid, NT, 0, st>>>(a);
@@ -1012,13 +1320,28 @@ int launch_audio_shape(const AudioArgs& a, bool vec, bool dbg, cudaStream_t st) 
 // Measured on B200 (profiles/r01f sweep, 1024 x 4 s): 128x16x4 0.84 ms, 256x16x2 0.86, 128x16x3 0.87, 256x8x3 0.93,
 // 128x8x6 0.95, 128x8x7 1.02.  16 samples per thread halve the per-tile scan/barrier cost; it needs T % 16 == 0 for
 // the 128-bit path (4 s: yes; 30 s: T % 8 == 0 only).
+#ifndef IAS_AUDIO_SP_DEFAULT
+#define IAS_AUDIO_SP_DEFAULT 1
+#endif
 AudioShape pick_shape(int T) {
-  AudioShape s = (T % 16 == 0) ? AudioShape{128, 16, 4} : AudioShape{128, 8, 6};
-  if (const char* e = getenv("IAS_VOICE_SHAPE")) {
+  AudioShape s = (T % 16 == 0) ? AudioShape{128, 16, 4, IAS_AUDIO_SP_DEFAULT} : AudioShape{128, 8, 6, 0};
+  if (const char* e = getenv("IAS_VOICE_SHAPE")) {  // "128x16x4" classic kernel, "p128x16x4" software-pipelined
     int nt = 0, spt = 0, c = 0;
-    if (sscanf(e, "%dx%dx%d", &nt, &spt, &c) == 3) s = AudioShape{nt, spt, c};
+    const int sp = e[0] == 'p' ? 1 : 0;
+    if (sscanf(e + (sp ? 1 : 0), "%dx%dx%d", &nt, &spt, &c) == 3) s = AudioShape{nt, spt, c, sp};
   }
   return s;
+}
+
+template <int NT, int SPT, int MINB>
+int launch_audio_sp(const AudioArgs& a, bool dbg, cudaStream_t st) {
+  const int grid = audio_grid(a.B, MINB);
+  ProfScope prof_(K_VOICE_AUDIO, st);
+  if (!dbg)
+    k_voice_audio_sp<NT, SPT, MINB, false><<<grid, NT, 0, st>>>(a);
+  else
+    k_voice_audio_sp<NT, SPT, MINB, true><<<grid, NT, 0, st>>>(a);
+  return IAS_OK;
 }
 
 int launch_audio(const AudioArgs& a, const VoiceWorkspace& w, bool dbg, bool schedule, bool audio, cudaStream_t st) {
@@ -1026,11 +1349,20 @@ int launch_audio(const AudioArgs& a, const VoiceWorkspace& w, bool dbg, bool sch
   const bool vec = (a.T % s.spt == 0) && ias_aligned16(a.noise) && ias_aligned16(a.audio);
   if (schedule) {
     ProfScope prof_(K_VOICE_SCHEDULE, st);
-    k_voice_schedule<<<1, SCHED_THREADS, 0, st>>>(a.vconst, a.B, a.T, a.scale, s.nt * s.spt, dbg ? 1 : 0, w.ntiles,
+    // IAS_VOICE_RENDER_ALL=1 (tuning runs): silent tails are rendered like any other tile (same audio: their gains
+    // are exactly 0), so every voice costs the same and a shape's throughput can be read without its load balance
+    static const bool render_all_env = getenv("IAS_VOICE_RENDER_ALL") != nullptr;
+    k_voice_schedule<<<1, SCHED_THREADS, 0, st>>>(a.vconst, a.B, a.T, a.scale, s.nt * s.spt,
+                                                  (dbg || render_all_env) ? 1 : 0, w.ntiles,
                                                   w.order, w.counter);
   }
   IAS_LAUNCH_CHECK("k_voice_schedule");
   if (!audio) return IAS_OK;
+#define IAS_SHAPE_SP(NT, SPT, MINB) \
+  if (s.sp == 1 && vec && s.nt == NT && s.spt == SPT && s.ctas_per_sm == MINB) { launch_audio_sp<NT, SPT, MINB>(a, dbg, st); } else
+  IAS_SHAPE_SP(128, 16, 4)
+  IAS_SHAPE_SP(128, 16, 3)
+#undef IAS_SHAPE_SP
 #define IAS_SHAPE(NT, SPT, MINB) \
   if (s.nt == NT && s.spt == SPT && s.ctas_per_sm == MINB) { launch_audio_shape<NT, SPT, MINB>(a, vec, dbg, st); } else
   IAS_SHAPE(128, 8, 7)

@@ -239,8 +239,14 @@ class Noise(SynthModule):
 class Voice(nn.Module):
     """torchsynth ``Voice`` rendered by ``libias_b200.so`` (``ias_voice_seed_params`` / ``ias_voice_render``)."""
 
-    def __init__(self, synthconfig: Optional[SynthConfig] = None, nebula: str = "default", normalize: bool = True):
+    def __init__(self, synthconfig: Optional[SynthConfig] = None, nebula: str = "default", normalize=True):
+        """``normalize``: True = torchsynth's normalize_if_clipping on the rendered audio (default), False = raw mix,
+        ``"defer"`` = raw mix plus ``self.row_scale`` [B] (1/peak of a clipping row, else 1) for a linear consumer to
+        apply -- ``PQMF.analysis(audio, row_scale=voice.row_scale)`` gives the bands of the normalised audio without
+        the second pass over the clipping rows (not a torchsynth option)."""
         super().__init__()
+        if normalize not in (True, False, "defer"):
+            raise ValueError("normalize must be True, False or 'defer'")
         if nebula != "default":
             raise ValueError("only the default nebula (torchsynth class defaults) is implemented")
         self.synthconfig = synthconfig if synthconfig is not None else SynthConfig()
@@ -387,6 +393,14 @@ class Voice(nn.Module):
                 _lib.current_stream(self.device))
         _lib.check(rc, "ias_voice_seed_params")
 
+    def _normalize_mode(self) -> int:
+        return 2 if self.normalize == "defer" else (1 if self.normalize else 0)
+
+    @property
+    def row_scale(self) -> Optional[torch.Tensor]:
+        """[B] factors of the last render when ``normalize == "defer"`` (else None)."""
+        return self._peak if self.normalize == "defer" else None
+
     def _frozen_rows(self) -> List[int]:
         return [1 if p.frozen else 0 for p in self._param_list()]
 
@@ -418,7 +432,7 @@ class Voice(nn.Module):
             rc = _lib.lib().ias_voice_render_stages(
                 _lib.ptr(self._store), _lib.ptr(noise), noise.shape[0], _lib.ptr(audio), _lib.ptr(self._peak),
                 cfg.batch_size, cfg.buffer_size, cfg.control_buffer_size, float(cfg.sample_rate),
-                float(cfg.control_rate), float(cfg.eps), 1 if self.normalize else 0, _lib.ptr(ctrl_in),
+                float(cfg.control_rate), float(cfg.eps), self._normalize_mode(), _lib.ptr(ctrl_in),
                 _lib.ptr(phase_debug), _lib.ptr(ws), ws.numel(), stages, _lib.current_stream(self.device))
         _lib.check(rc, "ias_voice_render_stages")
 
@@ -440,7 +454,7 @@ class Voice(nn.Module):
             rc = _lib.lib().ias_voice_render(
                 _lib.ptr(self._store), _lib.ptr(noise), noise.shape[0], _lib.ptr(audio), _lib.ptr(self._peak),
                 cfg.batch_size, cfg.buffer_size, cfg.control_buffer_size, float(cfg.sample_rate),
-                float(cfg.control_rate), float(cfg.eps), 1 if self.normalize else 0, _lib.ptr(ctrl_in),
+                float(cfg.control_rate), float(cfg.eps), self._normalize_mode(), _lib.ptr(ctrl_in),
                 _lib.ptr(phase_debug), _lib.ptr(ws), ws.numel(), _lib.current_stream(self.device))
         _lib.check(rc, "ias_voice_render")
         return (audio, self._peak) if return_peak else audio

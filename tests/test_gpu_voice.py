@@ -300,3 +300,71 @@ def test_gpu_voice_against_the_committed_oracle_fixture(cuda_device):
     err = np.abs(audio.cpu().numpy()[:, ::F.SUB_T] - want["audio"]).max(axis=1)
     print(f"vs fixture: median {np.median(err):.2e} max {err.max():.2e} voices <= 1e-4: {(err <= 1e-4).sum()}/{F.B}")
     assert np.median(err) <= 1e-5 and (err <= 1e-4).sum() >= int(0.8 * F.B)
+
+
+def _with_shape(shape, fn):
+    import os
+
+    old = os.environ.get("IAS_VOICE_SHAPE")
+    os.environ["IAS_VOICE_SHAPE"] = shape
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ["IAS_VOICE_SHAPE"]
+        else:
+            os.environ["IAS_VOICE_SHAPE"] = old
+
+
+def test_pipelined_audio_kernel_is_bit_identical_to_the_classic_one(config1, cuda_device):
+    """k_voice_audio_sp (pass 2 of tile t and pass 1 of tile t+1 in one block, the default for T % 16 == 0) runs the
+    same operations on the same operands as k_voice_audio: audio, peaks and both VCO phase arguments must agree bit
+    for bit, with the oracle's control signals and with the kernel's own, and with every voice rendered in full."""
+    voice, o = config1["voice"], config1["o"]
+    ctrl = o["ctrl"].contiguous().to(cuda_device)
+
+    def render(with_ctrl):
+        phase = torch.empty((128, 2, 176400), device=cuda_device)
+        audio, peak = voice.output(return_peak=True, phase_debug=phase, ctrl_in=ctrl if with_ctrl else None)
+        plain = voice.output()
+        return audio.clone(), peak.clone(), phase, plain.clone()
+
+    for with_ctrl in (True, False):
+        a0, p0, ph0, q0 = _with_shape("128x16x4", lambda: render(with_ctrl))
+        a1, p1, ph1, q1 = _with_shape("p128x16x4", lambda: render(with_ctrl))
+        assert torch.equal(_bits(ph0), _bits(ph1))
+        assert torch.equal(_bits(a0), _bits(a1)) and torch.equal(_bits(p0), _bits(p1))
+        assert torch.equal(_bits(q0), _bits(q1))  # the non-debug instantiation (silent tails skipped)
+        if not with_ctrl:  # rendering the silent tails gives the zeros that are otherwise filled in (up to -0)
+            assert torch.equal(q0, a0)
+    # the pipelined kernel against the torch CPU path directly (oracle control signals were the last render)
+    a1, p1, ph1, q1 = _with_shape("p128x16x4", lambda: render(True))
+    ph1 = ph1.cpu()
+    assert int((_bits(ph1[:, 0]) != _bits(o["arg1"])).sum()) == 0
+    assert int((_bits(ph1[:, 1]) != _bits(o["arg2"])).sum()) == 0
+
+
+def test_deferred_normalisation_matches_the_in_kernel_pass(config1, cuda_device):
+    """Voice(normalize="defer"): raw mix + row_scale; PQMF.analysis(row_scale=) gives the bands of the normalised
+    audio (linear filter bank) without the second pass over the clipping rows."""
+    import ias_b200
+
+    voice = config1["voice"]
+    audio, peak = voice.output(return_peak=True)
+    peak = peak.clone()
+    dv = ias_b200.Voice(synthconfig=voice.synthconfig, normalize="defer").to(cuda_device)
+    dv.load_state_dict(voice.state_dict())
+    raw = dv.output()
+    scale = dv.row_scale
+    clipped = peak > 1.0
+    assert int(clipped.sum()) > 0
+    assert torch.equal(scale[~clipped], torch.ones_like(scale[~clipped]))
+    assert float((scale[clipped] * peak[clipped] - 1.0).abs().max()) <= 1.2e-7  # RN(1/peak)
+    assert torch.equal(_bits(raw[~clipped]), _bits(audio[~clipped]))
+    assert float((raw * scale[:, None] - audio).abs().max()) <= 1.2e-7  # x * RN(1/p) vs RN(x / p): one ulp below 1
+    gram = ias_b200.PQMF(N=3).to(cuda_device)
+    want = gram(audio.unsqueeze(1))
+    got = gram.analysis(raw.unsqueeze(1), row_scale=scale)
+    assert float((got - want).abs().max() / want.abs().max()) <= 1e-6
+    with pytest.raises(ValueError):
+        ias_b200.Voice(synthconfig=voice.synthconfig, normalize="later")
