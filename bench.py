@@ -49,6 +49,12 @@ def parse():
                          "tests/test_gpu_e2e.py); --no-pipeline runs every stage of a batch back to back "
                          "(measured on B200: 1.249 vs 1.223 ms/step)")
     ap.set_defaults(pipeline=True)
+    ap.add_argument("--pipeline-depth", type=int, default=1, choices=[1, 2],
+                    help="1 (default): the whole control stage of batch k+1 under PQMF / bridge / loss of batch k; 2: the "
+                         "control stage in two halves -- LFO / modulation / records of batch k+1 under the PQMF analysis of "
+                         "batch k, then seeding + ADSR envelopes of batch k+2 under the bridge / loss kernels of batch k "
+                         "(bit-identical, measured slower: 1.133 vs 1.116 ms/step, the envelopes end up on the critical "
+                         "path of the step's join)")
     ap.add_argument("--gather", default="stats", choices=["stats", "peer", "nccl"],
                     help="N>1 embedding exchange: stats = every rank reduces its own rows and pushes a 0.4 MB summary "
                          "(mean, second moments, Gram) to its peers over NVLink from inside the loss kernels; peer = the "
@@ -70,6 +76,9 @@ def parse():
                          "read and written a second time; kernel = Voice(normalize=True): the audio tensor itself is "
                          "normalised by a second pass inside the render (what Voice.forward returns to a caller that wants "
                          "the audio)")
+    ap.add_argument("--main-priority", action="store_true",
+                    help="capture the step on a high-priority stream, so that the kernels of the batch in flight (PQMF, "
+                         "bridge, loss) are scheduled ahead of the next batch's control stage on the side stream")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (outside the timed region)")
     ap.add_argument("--parity-sounds", type=int, default=0,
                     help="sounds of the parity block's CPU oracle render (default: 128 at 4 s, 16 for long clips)")
@@ -469,13 +478,28 @@ def run_ours(args):
         audio, params, _ = voice(idx_dev, prepared=True)
         cur = torch.cuda.current_stream()
         pipe_side.wait_stream(cur)
-        with torch.cuda.stream(pipe_side):
+
+        def next_index():
             if next_from_host is not None:
-                idx_dev.copy_(next_from_host, non_blocking=True)   # H2D: the loader runs one batch ahead
+                idx_dev.copy_(next_from_host, non_blocking=True)   # H2D: the loader runs ahead of the render
             else:
                 idx_dev.add_(world)
-            voice.prepare(idx_dev)
-        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice.row_scale)
+
+        if args.pipeline_depth == 1:
+            with torch.cuda.stream(pipe_side):
+                next_index()
+                voice.prepare(idx_dev)
+            bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice.row_scale)
+        else:
+            with torch.cuda.stream(pipe_side):
+                voice.prepare_modulation()                         # batch k+1, under the PQMF analysis of batch k
+            analysis_done = torch.cuda.Event()
+            bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice.row_scale,
+                                                  after_analysis=lambda: analysis_done.record(cur))
+            with torch.cuda.stream(pipe_side):
+                pipe_side.wait_event(analysis_done)                # batch k+2: seed + envelopes, under bridge / loss
+                next_index()
+                voice.prepare_envelopes(idx_dev)
         with torch.no_grad():
             out = torch.stack(vic.loss(x, y))
         if result_to_host is not None:
@@ -483,9 +507,16 @@ def run_ours(args):
         cur.wait_stream(pipe_side)
         return out
 
-    def prime(first_batch: int):
+    def prime(first_batch: int, second_batch=None):
+        """Fill the pipeline: batch ``first_batch`` ready to render and, two deep, the envelopes of the batch after."""
         idx_dev.fill_(first_batch)
-        voice.prepare(idx_dev)
+        if args.pipeline_depth == 1:
+            voice.prepare(idx_dev)
+            return
+        voice.prepare_envelopes(idx_dev)
+        voice.prepare_modulation()
+        idx_dev.fill_(first_batch + world if second_batch is None else second_batch)
+        voice.prepare_envelopes(idx_dev)
 
     def capture(fn):
         """fn() captured in a CUDA graph (after a side-stream warm-up, as torch requires); None if capture fails."""
@@ -501,8 +532,14 @@ def run_ours(args):
             torch.cuda.current_stream().wait_stream(side)
             sync()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = fn()
+            if args.main_priority:
+                cap_stream = torch.cuda.Stream(device=dev, priority=-1)
+                cap_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.graph(g, stream=cap_stream):
+                    out = fn()
+            else:
+                with torch.cuda.graph(g):
+                    out = fn()
             idx_dev.copy_(keep)
             return g, out, "one CUDA graph replay per step"
         except Exception as exc:  # e.g. a collective that cannot be captured
@@ -521,7 +558,10 @@ def run_ours(args):
         prime(args.warmup * world + rank)
     graph_v, out_v, value_mode = capture(step_value)
     if pipelined:
-        value_mode += "; control stage of batch k+1 (Voice.prepare) overlapped with PQMF/bridge/loss of batch k"
+        value_mode += ("; control stage of batch k+1 (Voice.prepare) overlapped with PQMF/bridge/loss of batch k"
+                       if args.pipeline_depth == 1 else
+                       "; modulation stage of batch k+1 under the PQMF analysis of batch k, seeding + envelopes of batch "
+                       "k+2 under its bridge / loss kernels (Voice.prepare_modulation / prepare_envelopes)")
         prime(args.warmup * world + rank)
     else:
         idx_dev.fill_(args.warmup * world + rank)
@@ -596,17 +636,23 @@ def run_ours(args):
         return step_pipelined(next_from_host=host_in, result_to_host=host_out)
 
     step_e2e = step_e2e_pipelined if pipelined else step_e2e_plain
+
+    def prime_e2e():
+        prime(batch_numbers[0], batch_numbers[min(1, len(batch_numbers) - 1)])
+
     if pipelined:
         host_in[0] = batch_numbers[0]
-        prime(batch_numbers[0])
+        prime_e2e()
     graph, static_out, e2e_mode = capture(step_e2e)
     if pipelined:
-        e2e_mode += "; the loader runs one batch ahead: step k copies batch number k+1 in and prepares it on a side stream"
+        e2e_mode += ("; the loader runs %d batch(es) ahead: step k copies batch number k+%d in and prepares it on a side "
+                     "stream" % (args.pipeline_depth, args.pipeline_depth))
     stream = torch.cuda.current_stream()
 
     def run_e2e_step(j: int):
         # the DataLoader's integer arrives in pinned host memory: this step's batch (plain) or the next one's (pipelined)
-        host_in[0] = batch_numbers[min(j + 1, len(batch_numbers) - 1)] if pipelined else batch_numbers[j]
+        ahead = args.pipeline_depth if pipelined else 0
+        host_in[0] = batch_numbers[min(j + ahead, len(batch_numbers) - 1)]
         if graph is not None:
             graph.replay()
         else:
@@ -614,11 +660,11 @@ def run_ours(args):
         stream.synchronize()                           # the result is on the host: the step is over
 
     if pipelined:
-        prime(batch_numbers[0])
+        prime_e2e()
     for j in range(min(3, args.steps)):  # warm the replay path
         run_e2e_step(j)
     if pipelined:
-        prime(batch_numbers[0])
+        prime_e2e()
     sync()
     e0.record()
     for j in range(args.steps):
@@ -751,11 +797,13 @@ def run_ours(args):
                      "bound_pipe": mdl["bound_pipe"], "bound_cycles_per_sample": mdl["bound_cycles_per_sample"],
                      "achieved_frac": need / avail, "cycles_per_sample_measured": avail / (float(B) * T / 32.0),
                      "sm_mhz_used": clk, "schedulers": sms * 4,
-                     "note": "achieved_frac = cycles the busiest pipe (FMA) needs for B*T samples / (SMs x 4 schedulers x "
-                             "clock x measured launch time); an upper estimate: the ~11 % of samples in silent tails are "
-                             "zero-filled, not rendered.  The pipes overlap (tools/micro/dispatch_mix.cu), so 1.0 would be "
-                             "a kernel limited only by FMA-pipe throughput; the rest is dependent-issue latency at 4 warps "
-                             "per scheduler (DESIGN.md 3.1).  Per warp and sample; model: tools/issue_model.py"}
+                     "note": "achieved_frac = cycles the busiest issue-side resource (bound_pipe: the dispatch port, one "
+                             "warp instruction per cycle; the FMA pipe needs 95 %% of that) needs for B*T samples / (SMs x 4 "
+                             "schedulers x clock x measured launch time); an upper estimate: the ~11 %% of samples in silent "
+                             "tails are zero-filled, not rendered.  1.0 would be a kernel issuing one instruction per cycle "
+                             "and scheduler.  Occupancy scaling (1..4 CTAs per SM: 5.10 / 3.25 / 2.81 / 2.55 ms per 3552 "
+                             "full voices) and the variants with more warps or no serial section between tiles (all slower) "
+                             "are in DESIGN.md 3.1 / 3.2.  Per warp and sample; model: tools/issue_model.py" % ()}
     except Exception:
         pass
     try:
@@ -809,7 +857,7 @@ def run_ours(args):
                      "per-GPU batch in chunks of %d sounds)" % args.cpu_sample,
         },
         "roofline": {
-            "bound": "hbm", "kernel": "k_voice_audio", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": "k_voice_audio_sp (profiled as k_voice_audio)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": capture_note, "issue": issue,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": voice_bytes,
@@ -817,8 +865,8 @@ def run_ours(args):
                                                                " + 4*T*B noise read ([B,T] table, larger than L2)"),
             "frac_audio_write_only": 4.0 * T * B / (va["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
             "ms_per_launch": va["ms_per_launch"],
-            "note": "k_voice_audio is bound on the instruction side (dependent-issue latency at 4 warps per scheduler, see `issue`), "
-                    "not by HBM (DESIGN.md 3.1); step-level fraction below",
+            "note": "k_voice_audio_sp is bound on the instruction side (see `issue`), not by HBM (DESIGN.md 3.1); "
+                    "step-level fraction below",
             "step_frac": value / world * ALGO_BYTES_PER_SOUND * scale_T / 1e9 / hbm_peak,
             "step_algorithmic_bytes_per_sound": ALGO_BYTES_PER_SOUND * scale_T,
             "step_frac_with_noise_read": (None if args.reproducible else

@@ -52,10 +52,11 @@ def bridge(bands: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torc
 
 
 def analysis_bridge(gram, audio: torch.Tensor, params: torch.Tensor, wa: torch.Tensor, wp: torch.Tensor,
-                    row_scale: torch.Tensor | None = None):
+                    row_scale: torch.Tensor | None = None, after_analysis=None):
     """Device path of ``bridge(gram(audio), params)`` with the pooling fused into the PQMF analysis kernel
     (``PQMF.analysis_pooled``): the bands make one trip to HBM.  ``row_scale`` = ``Voice(normalize="defer").row_scale``
-    folds normalize_if_clipping into the analysis (the filter bank is linear).  -> (bands, x, y)."""
+    folds normalize_if_clipping into the analysis (the filter bank is linear).  ``after_analysis()`` is called once
+    the analysis kernel is enqueued (bench.py records an event there).  -> (bands, x, y)."""
     from ias_b200 import IasError, _lib
 
     global LAST_BRIDGE_PATH
@@ -68,10 +69,14 @@ def analysis_bridge(gram, audio: torch.Tensor, params: torch.Tensor, wa: torch.T
         if exc.code != _lib.IAS_ERR_UNSUPPORTED:
             raise
         bands = gram.analysis(x3, row_scale=row_scale)
+        if after_analysis is not None:
+            after_analysis()
         x, y = bridge(bands, params, wa, wp)
         LAST_BRIDGE_PATH = "unfused: ias_pqmf_analysis + ias_abs_avg_pool"
         return bands, x, y
     LAST_BRIDGE_PATH = "fused: ias_pqmf_analysis_pooled"
+    if after_analysis is not None:
+        after_analysis()
     return bands, feat @ wa, params @ wp
 
 

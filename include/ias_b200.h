@@ -103,9 +103,15 @@ IAS_API int ias_voice_render(const float* params01, const float* noise, int nois
 /* The same call split in two, so that a caller can overlap the (latency-bound) control stage of the NEXT batch with
  * whatever consumes the current audio: IAS_VOICE_STAGE_CONTROL runs ADSR + LFO/modulation + the work-queue schedule
  * from params01 into `workspace` (noise / audio / peak may be NULL); IAS_VOICE_STAGE_AUDIO renders the audio from a
- * workspace a control-stage call filled (params01 / ctrl_in unused).  Both bits = ias_voice_render. */
+ * workspace a control-stage call filled (params01 / ctrl_in unused).  Both bits = ias_voice_render.
+ * The control stage itself splits once more, for callers that pipeline two batches deep: IAS_VOICE_STAGE_ENVELOPES
+ * runs the six ADSR envelopes alone (compute bound: SLEEF-exact pow per control point), IAS_VOICE_STAGE_MODULATION
+ * the LFOs / modulation matrix / per-interval records / schedule from the envelopes a previous call left in the same
+ * workspace and the same params01.  ENVELOPES | MODULATION = CONTROL. */
 #define IAS_VOICE_STAGE_CONTROL 1
 #define IAS_VOICE_STAGE_AUDIO 2
+#define IAS_VOICE_STAGE_ENVELOPES 4
+#define IAS_VOICE_STAGE_MODULATION 8
 IAS_API int ias_voice_render_stages(const float* params01, const float* noise, int noise_rows, float* audio, float* peak,
                             int B, int T, int C, float sample_rate, float control_rate, float eps, int normalize,
                             const float* ctrl_in, float* phase_dbg, void* workspace, size_t workspace_bytes, int stages,

@@ -1169,7 +1169,11 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio_sp(AudioArgs A) {
       float lpeak = 0.0f;
       tot1 = 0;
       tot2 = 0;
+#ifdef IAS_AUDIO_COUNT_NOCLAMP_ONLY  // tools/issue_model.py: object for instruction counting only (never shipped)
+      if (true)
+#else
       if (noclamp)
+#endif
         merged_passes<SPT, false, DBG>(x1, x2, srcs, y, nzv, acc1, acc2, tot1, tot2, lpeak, V, ft0, fj, fj1, r1, r2, r3,
                                        ft0n, fjn, fj1n, r0n, r1n, dbg1, dbg2, t0, T);
       else
@@ -1255,15 +1259,16 @@ VoiceWorkspace carve(void* ws, int B, int C) {
   return w;
 }
 
+// envelopes: the six ADSR rows into the workspace; modulation: LFOs, modulation matrix, records (reads those rows)
 int launch_control(const float* params01, int B, int C, float cr, float eps, const float* ctrl_in, float* ctrl_out,
-                   const VoiceWorkspace& w, cudaStream_t st) {
+                   const VoiceWorkspace& w, cudaStream_t st, bool envelopes = true, bool modulation = true) {
   static const RangeTable ranges = make_range_table();
-  {
+  if (envelopes) {
     ProfScope prof_(K_VOICE_ADSR, st);
     k_voice_adsr<<<dim3(B, 6), ADSR_THREADS, 0, st>>>(params01, B, C, cr, eps, ranges, w.scratch);
   }
   IAS_LAUNCH_CHECK("k_voice_adsr");
-  {
+  if (modulation) {
     // 4 s clips: phase + output rows in shared memory (7*C floats); longer clips fall back to global scratch rows
     const size_t smem = (size_t)7 * C * sizeof(float);
     static unsigned long long attr_devs = 0;
@@ -1457,8 +1462,12 @@ extern "C" int ias_voice_render_stages(const float* params01, const float* noise
                                        float* peak, int B, int T, int C, float sample_rate, float control_rate,
                                        float eps, int normalize, const float* ctrl_in, float* phase_dbg,
                                        void* workspace, size_t workspace_bytes, int stages, ias_stream_t stream) {
-  const bool do_control = (stages & IAS_VOICE_STAGE_CONTROL) != 0, do_audio = (stages & IAS_VOICE_STAGE_AUDIO) != 0;
+  const bool do_env = (stages & (IAS_VOICE_STAGE_CONTROL | IAS_VOICE_STAGE_ENVELOPES)) != 0;
+  const bool do_mod = (stages & (IAS_VOICE_STAGE_CONTROL | IAS_VOICE_STAGE_MODULATION)) != 0;
+  const bool do_control = do_env || do_mod, do_audio = (stages & IAS_VOICE_STAGE_AUDIO) != 0;
   IAS_REQUIRE(do_control || do_audio, IAS_ERR_INVALID, "ias_voice_render: stages=%d selects nothing", stages);
+  IAS_REQUIRE(!(do_audio && do_env && !do_mod), IAS_ERR_INVALID,
+              "ias_voice_render: stages=%d renders audio from envelopes without the modulation stage", stages);
   if (!do_audio) {  // control stage only: the audio-side pointers are not used
     noise_rows = noise_rows > 0 ? noise_rows : 1;
   }
@@ -1476,7 +1485,7 @@ extern "C" int ias_voice_render_stages(const float* params01, const float* noise
   cudaStream_t st = as_stream(stream);
   VoiceWorkspace w = carve(workspace, B, C);
   if (do_control) {
-    int rc = launch_control(params01, B, C, control_rate, eps, ctrl_in, nullptr, w, st);
+    int rc = launch_control(params01, B, C, control_rate, eps, ctrl_in, nullptr, w, st, do_env, do_mod);
     if (rc) return rc;
   }
   AudioArgs a;
@@ -1495,5 +1504,5 @@ extern "C" int ias_voice_render_stages(const float* params01, const float* noise
   a.rsr = 1.0f / sample_rate;
   a.normalize = normalize;
   // the work queue (k_voice_schedule) belongs to the control stage: it depends on the control signals only
-  return launch_audio(a, w, phase_dbg != nullptr, do_control, do_audio, st);
+  return launch_audio(a, w, phase_dbg != nullptr, do_mod, do_audio, st);
 }

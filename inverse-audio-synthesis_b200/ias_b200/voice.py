@@ -404,7 +404,7 @@ class Voice(nn.Module):
     def _frozen_rows(self) -> List[int]:
         return [1 if p.frozen else 0 for p in self._param_list()]
 
-    STAGE_CONTROL, STAGE_AUDIO = 1, 2
+    STAGE_CONTROL, STAGE_AUDIO, STAGE_ENVELOPES, STAGE_MODULATION = 1, 2, 4, 8
 
     def prepare(self, batch_idx) -> None:
         """Seed the parameters of batch ``batch_idx`` and run the control stage (envelopes, LFOs, modulation, work
@@ -419,6 +419,36 @@ class Voice(nn.Module):
             self.randomize(seed=batch_idx if on_device else int(batch_idx))
             self._render(self.STAGE_CONTROL, None)
         self._prepared = batch_idx if on_device else int(batch_idx)
+        self._snap_valid = False
+
+    def prepare_envelopes(self, batch_idx) -> None:
+        """First half of ``prepare`` for callers that pipeline two batches deep: seed the parameters of ``batch_idx``
+        and run its six ADSR envelopes (compute bound) into the workspace.  ``prepare_modulation()`` completes the
+        control stage later.  Between the two calls the parameter store holds this batch; a batch whose modulation
+        stage already ran keeps its parameters in a snapshot, so it may still be waiting for its audio stage."""
+        if batch_idx is None:
+            raise ValueError("Voice.prepare_envelopes needs a batch index")
+        on_device = isinstance(batch_idx, torch.Tensor) and batch_idx.is_cuda
+        with torch.no_grad():
+            self.randomize(seed=batch_idx if on_device else int(batch_idx))
+            self._render(self.STAGE_ENVELOPES, None)
+        self._enveloped = batch_idx if on_device else int(batch_idx)
+
+    def prepare_modulation(self) -> None:
+        """Second half of ``prepare``: LFOs, modulation matrix, per-interval records and the work queue of the batch
+        ``prepare_envelopes`` seeded; snapshots its parameters / train flags (the store is reseeded before this batch
+        is rendered).  ``forward(batch_idx, prepared=True)`` then renders it."""
+        want = getattr(self, "_enveloped", None)
+        if want is None:
+            raise RuntimeError("Voice.prepare_modulation: no batch has its envelopes prepared")
+        with torch.no_grad():
+            self._render(self.STAGE_MODULATION, None)
+            if getattr(self, "_params_snap", None) is None or self._params_snap.device != self.device:
+                self._params_snap = torch.empty((self.batch_size, _lib.NPARAMS), dtype=torch.float32, device=self.device)
+                self._is_train_snap = torch.empty_like(self._is_train)
+            self._params_snap.copy_(self._store.t())
+            self._is_train_snap.copy_(self._is_train)
+        self._prepared, self._enveloped, self._snap_valid = want, None, True
 
     def _render(self, stages: int, audio: Optional[torch.Tensor], phase_debug=None, ctrl_in=None):
         cfg = self.synthconfig
@@ -494,8 +524,12 @@ class Voice(nn.Module):
                 raise RuntimeError(f"Voice.forward(prepared=True): batch {batch_idx} was not prepared (have {want})")
             self._prepared = None
             with ctx:
-                is_train = self._is_train.bool()
-                params = self._store.t().contiguous()
+                if getattr(self, "_snap_valid", False):  # prepared in two halves: the store may hold the batch after
+                    is_train = self._is_train_snap.bool()
+                    params = self._params_snap.clone()
+                else:
+                    is_train = self._is_train.bool()
+                    params = self._store.t().contiguous()
                 cfg = self.synthconfig
                 audio = torch.empty((cfg.batch_size, cfg.buffer_size), dtype=torch.float32, device=self.device)
                 self._render(self.STAGE_AUDIO, audio)

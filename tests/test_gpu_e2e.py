@@ -234,3 +234,83 @@ def test_prepared_batches_render_bit_identically(cuda_device):
         torch.cuda.synchronize()
         for got, ref in zip(out, want[n]):
             assert torch.equal(got, ref)
+
+
+def test_two_deep_pipeline_renders_bit_identically(cuda_device):
+    """The control stage in two halves, two batches ahead (bench.py --pipeline-depth 2): modulation stage of batch k+1
+    under the analysis of batch k, seeding + ADSR envelopes of batch k+2 after it.  Audio, parameters, is_train and the
+    loss of every batch equal the unpipelined render bit for bit, eagerly and from a CUDA graph; the deferred
+    normalisation factors ride along."""
+    import ias_b200
+
+    B = 32
+    cfg = ias_b200.SynthConfig(batch_size=B, reproducible=True, sample_rate=44100, buffer_size_seconds=4.0)
+    voice = ias_b200.Voice(synthconfig=cfg, normalize="defer").to(cuda_device)
+    gram = ias_b200.PQMF(N=3).to(cuda_device)
+    vcfg = types.SimpleNamespace(dim=256, embeddim=256, vicreg=types.SimpleNamespace(
+        mlp="8-8-%d", batch_size=B, sim_coeff=25.0, std_coeff=25.0, cov_coeff=1.0))
+    vic = ias_b200.VICReg(vcfg, torch.nn.Identity(), torch.nn.Identity())
+    wa, wp = harness.bridge_weights(cuda_device)
+    side = torch.cuda.Stream(device=cuda_device)
+
+    def tail(audio, params, hook=None):
+        bands, x, y = harness.analysis_bridge(gram, audio, params, wa, wp, voice.row_scale, after_analysis=hook)
+        with torch.no_grad():
+            return torch.stack(vic.loss(x, y))
+
+    batches = [4, 5, 6, 7, 8]
+    want = []
+    for k in batches:
+        audio, params, is_train = voice(k)
+        want.append((audio.clone(), params.clone(), is_train.clone(), tail(audio, params).clone()))
+
+    with pytest.raises(RuntimeError):
+        voice.prepare_modulation()  # nothing enveloped yet
+    idx = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+
+    def prime():
+        idx.fill_(batches[0])
+        voice.prepare_envelopes(idx)
+        voice.prepare_modulation()
+        idx.add_(1)
+        voice.prepare_envelopes(idx)
+
+    def step():
+        audio, params, is_train = voice(idx, prepared=True)
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            voice.prepare_modulation()
+        done = torch.cuda.Event()
+        loss = tail(audio, params, hook=lambda: done.record(cur))
+        with torch.cuda.stream(side):
+            side.wait_event(done)
+            idx.add_(1)
+            voice.prepare_envelopes(idx)
+        cur.wait_stream(side)
+        return audio, params, is_train, loss
+
+    prime()
+    for n in range(len(batches)):
+        out = step()
+        torch.cuda.synchronize()
+        for got, ref in zip(out, want[n]):
+            assert torch.equal(got, ref)
+
+    prime()
+    warm = torch.cuda.Stream(device=cuda_device)
+    warm.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(warm):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(warm)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step()
+    prime()
+    for n in range(len(batches)):
+        g.replay()
+        torch.cuda.synchronize()
+        for got, ref in zip(out, want[n]):
+            assert torch.equal(got, ref)

@@ -30,7 +30,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 CSRC = os.path.join(ROOT, "inverse-audio-synthesis_b200", "csrc")
-KERNEL = r"k_voice_audioILi128ELi16ELi4ELb1ELb0"
+KERNEL = r"k_voice_audio_spILi128ELi16ELi4ELb0"  # the default audio kernel (software-pipelined)
 SPT = 16
 PACKED = {"FFMA2", "FADD2", "FMUL2"}
 SCALAR_FP32 = {"FFMA", "FADD", "FMUL"}
@@ -79,7 +79,7 @@ def main():
     }
     bound = max(pipes, key=pipes.get)
     out = {
-        "kernel": "k_voice_audio<128,16,4> tile loop, no-clamp path (85 % of voices)",
+        "kernel": "k_voice_audio_sp<128,16,4> tile loop (pass 2 of tile t + pass 1 of tile t+1), no-clamp path (85 % of voices)",
         "src_sha256": bench.source_hash(),
         "warp_instructions_per_tile": len(body),
         "instr_per_sample": len(body) / SPT,
