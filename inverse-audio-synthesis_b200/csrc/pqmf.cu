@@ -271,6 +271,23 @@ __device__ __forceinline__ void load_window(const float* __restrict__ src, float
   }
 }
 
+// Row (sound) and tile of a CTA.  The launchers use a 2-D grid (x = tile, y = row) whenever the batch fits gridDim.y:
+// a 1-D grid costs every CTA an integer division by a kernel argument -- I2F, MUFU.RCP, F2I and a dozen dependent
+// integer instructions before the tile's bulk copy can be issued (12 % of the analysis kernel's stall samples sat on
+// that chain, profiles/r3z).  Batches beyond 65535 rows keep the 1-D grid and the division.
+__device__ __forceinline__ void row_and_tile(int tiles_per_row, int& b, int& tile) {
+  if (gridDim.x == (unsigned)tiles_per_row) {
+    b = blockIdx.y;
+    tile = blockIdx.x;
+  } else {
+    b = blockIdx.x / tiles_per_row;
+    tile = blockIdx.x - b * tiles_per_row;
+  }
+}
+inline dim3 row_tile_grid(int B, int tiles) {
+  return B <= 65535 ? dim3((unsigned)tiles, (unsigned)B) : dim3((unsigned)((size_t)B * tiles));
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // analysis: out[b][k][n] = sum_j H[k][j] * x[b][n*N + j - PAD]
 // ------------------------------------------------------------------------------------------------------------
@@ -289,8 +306,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   __shared__ __align__(16) float xs[Pad<S>::floats(SPAN4 * 4)];
   __shared__ int s_bound[POOL ? N : 1][3];                        // per band: start of bin ilo+1, end of bin ilo, ilo
 
-  const int b = blockIdx.x / tiles_per_row;
-  const int tile = blockIdx.x - b * tiles_per_row;
+  int b, tile;
+  row_and_tile(tiles_per_row, b, tile);
   const int n_tile = tile * TILE_N;
   const float scale = row_scale ? row_scale[b] : 1.0f;
   const int g0 = n_tile * N - PAD - OFF;  // multiple of 4
@@ -583,8 +600,8 @@ k_pqmf_synthesis(const float* __restrict__ z, float* __restrict__ y, int L, int 
   constexpr int ROW = Pad<Q>::floats(SPAN4 * 4);
   __shared__ __align__(16) float zs[N * ROW];
 
-  const int b = blockIdx.x / tiles_per_row;
-  const int tile = blockIdx.x - b * tiles_per_row;
+  int b, tile;
+  row_and_tile(tiles_per_row, b, tile);
   const int n_tile = tile * TILE_N;
   const int g0 = n_tile + DMIN - OFF;  // multiple of 4
   const bool vec_ok = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
@@ -674,8 +691,8 @@ k_pqmf_synthesis_cm(const float* __restrict__ z, float* __restrict__ y, int L, i
   static_assert(N % 4 == 0, "128-bit rows");
   __shared__ __align__(16) float vs[PQ_THREADS * PITCH];
 
-  const int b = blockIdx.x / tiles_per_row;
-  const int tile = blockIdx.x - b * tiles_per_row;
+  int b, tile;
+  row_and_tile(tiles_per_row, b, tile);
   const int n_tile = tile * TILE_N;
 
   {
@@ -797,8 +814,8 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
   constexpr int UNITS = ROWS + ROWS / Q + 1;
   __shared__ __align__(16) float vs[2 * UNITS * 4];
 
-  const int b = blockIdx.x / tiles_per_row;
-  const int tile = blockIdx.x - b * tiles_per_row;
+  int b, tile;
+  row_and_tile(tiles_per_row, b, tile);
   const int n_tile = tile * TILE_N;
   const float* zb = z + (size_t)b * N * L;
 
@@ -917,7 +934,7 @@ int launch_analysis(const float* x, const float* H_host, const float* proto_host
                     int L, cudaStream_t st, const PoolReq* pr = nullptr) {
   constexpr int TILE_N = PQ_THREADS * Q;
   const int tiles = (L + TILE_N - 1) / TILE_N;
-  const unsigned grid = (unsigned)((size_t)B * tiles);
+  const dim3 grid = row_tile_grid(B, tiles);
   PoolArgs pool{nullptr, 0, 0, 0, 0, 0, 0};
   if (pr) {
     const long long S = (long long)N * L;
@@ -991,7 +1008,7 @@ int launch_synthesis(const float* z, const float* G_host, float* y, int B, int L
   const int tiles = (L + TILE_N - 1) / TILE_N;
   {
     ProfScope prof_(K_PQMF_SYNTHESIS, st);
-    k_pqmf_synthesis<N, K, Q><<<(unsigned)((size_t)B * tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+    k_pqmf_synthesis<N, K, Q><<<row_tile_grid(B, tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
   }
   IAS_LAUNCH_CHECK("k_pqmf_synthesis");
   return IAS_OK;
@@ -1009,7 +1026,7 @@ int launch_synthesis_cm(const float* z, const float* proto_host, float* y, int B
   const int tiles = (L + TILE_N - 1) / TILE_N;
   {
     ProfScope prof_(K_PQMF_SYNTHESIS, st);
-    k_pqmf_synthesis_cm<N, K><<<(unsigned)((size_t)B * tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+    k_pqmf_synthesis_cm<N, K><<<row_tile_grid(B, tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
   }
   IAS_LAUNCH_CHECK("k_pqmf_synthesis_cm");
   return IAS_OK;
@@ -1027,7 +1044,7 @@ int launch_synthesis_small(const float* z, const float* proto_host, float* y, in
   const int tiles = (L + TILE_N - 1) / TILE_N;
   {
     ProfScope prof_(K_PQMF_SYNTHESIS, st);
-    k_pqmf_synthesis_small<N, K, Q><<<(unsigned)((size_t)B * tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+    k_pqmf_synthesis_small<N, K, Q><<<row_tile_grid(B, tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
   }
   IAS_LAUNCH_CHECK("k_pqmf_synthesis_small");
   return IAS_OK;
