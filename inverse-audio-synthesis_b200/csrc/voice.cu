@@ -941,6 +941,10 @@ __global__ void __launch_bounds__(NT, MINB) k_voice_audio(AudioArgs A) {
 // classic kernel keeps 32 converted doubles = 64 registers alive across the barrier); the widening is two integer
 // instructions instead of an XU-pipe F2F (increments are positive normal numbers).  Same operations on the same
 // operands in the same order per sample: audio is bit-identical to k_voice_audio (tests/test_gpu_voice.py).
+// Measured (profiles/r3_audio_experiments.md): 0.718 -> 0.706 ms, issue slots 54 -> 60 % busy.  The three switches
+// below are the variants that were timed against it (F2F widening 0.726 ms, recomputed source coordinates 0.714,
+// pitch chain first in source order 0.737); the last-tile threads past the end of the clip and the block's pass 1 of
+// the tile after the last one compute on extrapolated control values -- finite or not, nothing reads them.
 #ifndef IAS_SP_F2D_BITS
 #define IAS_SP_F2D_BITS 1
 #endif
