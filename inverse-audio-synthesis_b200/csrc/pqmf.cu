@@ -908,6 +908,170 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// synthesis, N = 3 (the reference's bank, vicreg_audio_params.py:40), cosine-modulated form in packed fp32 (FFMA2):
+// same rows, same taps and the same accumulation order per output as k_pqmf_synthesis_small<3>, so the results are
+// bit-identical to it.  That kernel is bound by the shared-memory / L1 data pipe (58 B of traffic per 4-byte output),
+// not by instruction issue, so the point of the packing is the LAYOUT it allows: 24 instead of 32 bytes per row.
+// The three taps that meet (time step q, row i), d = i - q, are j = 3d-1, 3d, 3d+1 on output phases 2, 1, 0 and read
+// elements 0, 1, 2 of row half d & 1.  Two of them are adjacent in the row and in the tap table:
+//   (y[q][2], y[q][1]) += (g[3d-1], g[3d]) * (half[0], half[1])
+// and the third is paired with the neighbouring time step, which reads the OTHER half of the same row:
+//   (y[q][0], y[q+1][0]) += (g[3d+1], g[3d-2]) * (half_d[2], half_{d-1}[2])          (q even)
+// For even q the parity of d is the parity of the row index (Q is even), so a row is only ever read with one order
+// of that pair and stores it in that order:
+//   plane 0, 16 bytes per row: a0 a1 | b0 b1          plane 1, 8 bytes per row: a2 b2 (even rows) / b2 a2 (odd rows)
+// (a = half 0, b = half 1): one 128-bit and one 64-bit shared load per row, every operand an aligned register pair.
+// Taps outside [0, K) are zeros of the pair tables (their products add +0 to a finite accumulator).
+// ------------------------------------------------------------------------------------------------------------
+template <int K>
+struct TapsSynN3P {
+  static constexpr int ND = SynRows<3, K>::HALO + 1;
+  // modulation pairs per band k: with c[k][r] as TapsSynSmall<3, K>::c and a_e = c[k][res(0, e)], b_e = c[k][res(1, e)]:
+  // (a0, a1), (b0, b1), (a2, b2), (b2, a2)
+  float2 cp[3 * 4];
+  float2 ga[ND];    // (g[3d-1], g[3d])
+  float2 gc[ND];    // (g[3d+1], g[3d-2])
+};
+
+template <int K, int Q>
+__global__ void __launch_bounds__(PQ_THREADS)
+k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, int tiles_per_row, TapsSynN3P<K> taps) {
+  constexpr int N = 3;
+  using R = SynRows<N, K>;
+  constexpr int DMIN = R::DMIN, HALO = R::HALO;
+  static_assert(R::jb(DMIN) == -1 && Q % 2 == 0, "pair tables assume taps 3d-1 .. 3d+1 and an even Q");
+  static_assert(PQ_THREADS % Q == 0, "phase-1 store offsets");
+  constexpr int TILE_N = PQ_THREADS * Q;
+  constexpr int ROWS = TILE_N + HALO;
+  constexpr int PASSES = (ROWS + PQ_THREADS - 1) / PQ_THREADS;
+  // Row r lives at unit r + r/Q of both planes (16-byte units in plane 0, 8-byte units in plane 1): lane t of phase 2
+  // reads rows Q t + i, i.e. units (Q + 1) t + const with Q + 1 odd -- conflict free for both widths, offsets are
+  // compile-time constants; phase 1 (lane = consecutive rows) is conflict free in plane 0 and has one 2-way pair per
+  // half warp in plane 1.
+  constexpr int UNITS = ROWS + ROWS / Q + 1;
+  __shared__ __align__(16) float vs[UNITS * 4 + UNITS * 2];
+  float* const plane1 = vs + UNITS * 4;
+
+  int b, tile;
+  row_and_tile(tiles_per_row, b, tile);
+  const int n_tile = tile * TILE_N;
+  const float* zb = z + (size_t)b * N * L;
+
+  // ---- phase 1: modulate rows n_tile + DMIN + [0, ROWS) ----
+  float zk[PASSES][N];
+  if (n_tile + DMIN >= 0 && n_tile + DMIN + ROWS <= L) {
+    // interior tile (all but the first and last of a sound): one pointer per band, constant offsets, no bounds logic
+    const float* p0 = zb + (n_tile + DMIN + (int)threadIdx.x);
+    const float* p1 = p0 + L;
+    const float* p2_ = p1 + L;
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i)
+      if ((i + 1) * PQ_THREADS <= ROWS || (int)threadIdx.x + i * PQ_THREADS < ROWS) {
+        zk[i][0] = __ldg(p0 + i * PQ_THREADS);
+        zk[i][1] = __ldg(p1 + i * PQ_THREADS);
+        zk[i][2] = __ldg(p2_ + i * PQ_THREADS);
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      const int row = (int)threadIdx.x + i * PQ_THREADS;
+      const int m = n_tile + DMIN + row;
+      const bool in = row < ROWS && m >= 0 && m < L;
+#pragma unroll
+      for (int k = 0; k < N; ++k) zk[i][k] = in ? __ldg(zb + (size_t)k * L + m) : 0.0f;
+    }
+  }
+  {
+    // this thread's rows all have the parity of threadIdx.x (PQ_THREADS is even): order of the (a2, b2) pair
+    const bool odd = (threadIdx.x & 1) != 0;
+    P2 cx[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float2 e = taps.cp[k * 4 + 2], o = taps.cp[k * 4 + 3];
+      cx[k] = odd ? p2(o.x, o.y) : p2(e.x, e.y);
+    }
+    const int unit0 = (int)threadIdx.x + (int)threadIdx.x / Q;
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      if ((i + 1) * PQ_THREADS <= ROWS || (int)threadIdx.x + i * PQ_THREADS < ROWS) {
+        // the stored pairs straight from packed multiply-adds (same k order per value as the scalar kernel)
+        P2 va = p2(0.0f, 0.0f), vb = va, vx = va;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const P2 zz = p2(zk[i][k], zk[i][k]);
+          const float2 ca = taps.cp[k * 4 + 0], cb = taps.cp[k * 4 + 1];
+          va = p2_fma(p2(ca.x, ca.y), zz, va);
+          vb = p2_fma(p2(cb.x, cb.y), zz, vb);
+          vx = p2_fma(cx[k], zz, vx);
+        }
+        // row / Q = threadIdx.x / Q + i * (PQ_THREADS / Q): the pass offset is a compile-time constant
+        const int unit = unit0 + i * (PQ_THREADS + PQ_THREADS / Q);
+        *reinterpret_cast<ulonglong2*>(vs + unit * 4) = make_ulonglong2(va.v, vb.v);
+        *reinterpret_cast<unsigned long long*>(plane1 + unit * 2) = vx.v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: Q time steps per thread, rows streamed once, two multiply-adds per instruction ----
+  const int n0 = n_tile + (int)threadIdx.x * Q;
+  if (n0 >= L) return;
+  P2 acc21[Q];      // (y[q][2], y[q][1])
+  P2 acc00[Q / 2];  // (y[2 q2][0], y[2 q2 + 1][0])
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc21[q] = p2(0.0f, 0.0f);
+#pragma unroll
+  for (int q = 0; q < Q / 2; ++q) acc00[q] = p2(0.0f, 0.0f);
+  const int ubase = (int)threadIdx.x * (Q + 1);  // unit of row threadIdx.x * Q
+#pragma unroll
+  for (int i = 0; i < Q + HALO; ++i) {
+    const int unit = ubase + i + i / Q;
+    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(vs + unit * 4);
+    P2 half[2];
+    half[0].v = t.x;
+    half[1].v = t.y;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int d = i - q;
+      if (d >= 0 && d <= HALO) {
+        const float2 g = taps.ga[d];
+        acc21[q] = p2_fma(half[d & 1], p2(g.x, g.y), acc21[q]);
+      }
+    }
+    P2 x;
+    x.v = *reinterpret_cast<const unsigned long long*>(plane1 + unit * 2);
+#pragma unroll
+    for (int q2 = 0; q2 < Q / 2; ++q2) {
+      const int d = i - 2 * q2;  // step 2 q2 meets this row at d, step 2 q2 + 1 at d - 1 (tap 0 in gc[0].y)
+      if (d >= 0 && d <= HALO) {
+        const float2 g = taps.gc[d];
+        acc00[q2] = p2_fma(x, p2(g.x, g.y), acc00[q2]);
+      }
+    }
+  }
+
+  float flat[Q * N];
+#pragma unroll
+  for (int q2 = 0; q2 < Q / 2; ++q2) {
+    p2_unpack(acc00[q2], flat[(2 * q2) * N], flat[(2 * q2 + 1) * N]);
+    p2_unpack(acc21[2 * q2], flat[(2 * q2) * N + 2], flat[(2 * q2) * N + 1]);
+    p2_unpack(acc21[2 * q2 + 1], flat[(2 * q2 + 1) * N + 2], flat[(2 * q2 + 1) * N + 1]);
+  }
+  float* yo = y + (size_t)b * L * N + (size_t)n0 * N;
+  const bool st_vec = (((size_t)L * N) % 4 == 0) && ((Q * N) % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+  if (st_vec && n0 + Q <= L) {
+    store_run<Q * N>(yo, flat, (reinterpret_cast<uintptr_t>(yo) & 31u) == 0);
+  } else {
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+      if (n0 + q < L) {
+#pragma unroll
+        for (int p = 0; p < N; ++p) yo[q * N + p] = flat[q * N + p];
+      }
+  }
+}
+
 __global__ void k_pqmf_synthesis_generic(const float* __restrict__ z, const float* __restrict__ G,
                                          float* __restrict__ y, int B, int L, int N, int K) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1047,6 +1211,37 @@ int launch_synthesis_small(const float* z, const float* proto_host, float* y, in
     k_pqmf_synthesis_small<N, K, Q><<<row_tile_grid(B, tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
   }
   IAS_LAUNCH_CHECK("k_pqmf_synthesis_small");
+  return IAS_OK;
+}
+
+template <int K, int Q>
+int launch_synthesis_n3p(const float* z, const float* proto_host, float* y, int B, int L, cudaStream_t st) {
+  constexpr int N = 3;
+  TapsSynN3P<K> taps;
+  using R = SynRows<N, K>;
+  for (int k = 0; k < N; ++k) {
+    auto c = [&](int h, int e) {
+      const int r = R::res(h, e);
+      return (float)(N * cos((2.0 * k + 1.0) * (3.14159265358979323846 / (2.0 * N)) * (r - (K - 2) / 2.0) -
+                             ((k & 1) ? -1.0 : 1.0) * 3.14159265358979323846 / 4.0));
+    };
+    taps.cp[k * 4 + 0] = make_float2(c(0, 0), c(0, 1));
+    taps.cp[k * 4 + 1] = make_float2(c(1, 0), c(1, 1));
+    taps.cp[k * 4 + 2] = make_float2(c(0, 2), c(1, 2));
+    taps.cp[k * 4 + 3] = make_float2(c(1, 2), c(0, 2));
+  }
+  auto g = [&](int j) { return (j >= 0 && j < K) ? proto_host[j] : 0.0f; };
+  for (int d = 0; d < TapsSynN3P<K>::ND; ++d) {
+    taps.ga[d] = make_float2(g(3 * d - 1), g(3 * d));
+    taps.gc[d] = make_float2(g(3 * d + 1), g(3 * d - 2));
+  }
+  constexpr int TILE_N = PQ_THREADS * Q;
+  const int tiles = (L + TILE_N - 1) / TILE_N;
+  {
+    ProfScope prof_(K_PQMF_SYNTHESIS, st);
+    k_pqmf_synthesis_n3p<K, Q><<<row_tile_grid(B, tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_synthesis_n3p");
   return IAS_OK;
 }
 
@@ -1202,8 +1397,13 @@ extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const floa
         return launch_synthesis_small<4, 63, 4>(z, proto_host, y, B, L, st);  // measured: Q=4 0.411 ms, Q=8 0.471, direct 0.643
       }
       if (N == 3) {
+        const char* pk = getenv("IAS_PQMF_SYNTH_PACKED");  // tuning switch: 0 = scalar FIR phase (bit-identical results)
+        if (!pk || atoi(pk) != 0) {
+          if (q_env == 4) return launch_synthesis_n3p<63, 4>(z, proto_host, y, B, L, st);
+          return launch_synthesis_n3p<63, 8>(z, proto_host, y, B, L, st);
+        }
         if (q_env == 4) return launch_synthesis_small<3, 63, 4>(z, proto_host, y, B, L, st);
-        return launch_synthesis_small<3, 63, 8>(z, proto_host, y, B, L, st);  // measured: Q=8 0.439 ms, Q=4 0.485, direct 0.494
+        return launch_synthesis_small<3, 63, 8>(z, proto_host, y, B, L, st);  // measured: Q=8 0.345 ms, Q=4 0.485, direct 0.494
       }
       if (N == 2) return launch_synthesis_small<2, 63, 4>(z, proto_host, y, B, L, st);
     }
