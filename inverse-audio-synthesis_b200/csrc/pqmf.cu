@@ -924,6 +924,29 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
 // (a = half 0, b = half 1): one 128-bit and one 64-bit shared load per row, every operand an aligned register pair.
 // Taps outside [0, K) are zeros of the pair tables (their products add +0 to a finite accumulator).
 // ------------------------------------------------------------------------------------------------------------
+// tuning builds (tools/gpu_r4e.sh, one box, 1024 x 4 s): plane-1 padding every Q rows as in plane 0 (PAD1=0) / register
+// cap through __launch_bounds__(128, MINB) / static shared memory.  Measured: uncapped (75 registers, 6 CTAs per SM)
+// 0.288 ms; MINB=7 (70 registers, 7 CTAs per SM) 0.324 ms -- ptxas pays for the five registers with a serialised load
+// schedule that costs far more than the seventh CTA brings; MINB=7 with PAD1=0 0.318; static instead of dynamic shared
+// memory: no difference.
+#ifndef IAS_SYN3_PAD1
+#define IAS_SYN3_PAD1 1
+#endif
+#ifndef IAS_SYN3_MINB
+#define IAS_SYN3_MINB 1
+#endif
+#ifndef IAS_SYN3_STATIC
+#define IAS_SYN3_STATIC 0
+#endif
+template <int K, int Q>
+struct SynN3PSmem {
+  static constexpr int ROWS = PQ_THREADS * Q + SynRows<3, K>::HALO;
+  static constexpr int UNITS = ROWS + ROWS / Q + 1;         // plane 0: 16-byte units, row r at unit r + r/Q
+  static constexpr int PADQ1 = IAS_SYN3_PAD1 ? 2 * Q : Q;
+  static constexpr int UNITS1 = ROWS + ROWS / PADQ1 + 1;  // plane 1: 8-byte units, row r at unit r + r/(2Q)
+  static constexpr size_t BYTES = (size_t)UNITS * 16 + (size_t)UNITS1 * 8;
+};
+
 template <int K>
 struct TapsSynN3P {
   static constexpr int ND = SynRows<3, K>::HALO + 1;
@@ -934,23 +957,35 @@ struct TapsSynN3P {
   float2 gc[ND];    // (g[3d+1], g[3d-2])
 };
 
-template <int K, int Q>
-__global__ void __launch_bounds__(PQ_THREADS)
+template <int K, int Q, int MINB>
+__global__ void __launch_bounds__(PQ_THREADS, MINB)
 k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, int tiles_per_row, TapsSynN3P<K> taps) {
   constexpr int N = 3;
   using R = SynRows<N, K>;
   constexpr int DMIN = R::DMIN, HALO = R::HALO;
   static_assert(R::jb(DMIN) == -1 && Q % 2 == 0, "pair tables assume taps 3d-1 .. 3d+1 and an even Q");
-  static_assert(PQ_THREADS % Q == 0, "phase-1 store offsets");
+  static_assert(PQ_THREADS % (2 * Q) == 0, "phase-1 store offsets");
   constexpr int TILE_N = PQ_THREADS * Q;
   constexpr int ROWS = TILE_N + HALO;
   constexpr int PASSES = (ROWS + PQ_THREADS - 1) / PQ_THREADS;
-  // Row r lives at unit r + r/Q of both planes (16-byte units in plane 0, 8-byte units in plane 1): lane t of phase 2
-  // reads rows Q t + i, i.e. units (Q + 1) t + const with Q + 1 odd -- conflict free for both widths, offsets are
-  // compile-time constants; phase 1 (lane = consecutive rows) is conflict free in plane 0 and has one 2-way pair per
-  // half warp in plane 1.
-  constexpr int UNITS = ROWS + ROWS / Q + 1;
-  __shared__ __align__(16) float vs[UNITS * 4 + UNITS * 2];
+  // phase-1 passes whose loads are issued before any arithmetic: all of them up to Q = 8 (measured: chunks of 4 passes
+  // save 6 registers and cost 4 %: 0.327 against 0.314 ms -- the phase waits on those loads), chunks of 4 beyond
+  constexpr int CH = Q <= 8 ? PASSES : 4;
+  // Plane 0 (16-byte units): row r at unit r + r/Q.  Lane t of phase 2 reads rows Q t + i, i.e. units (Q + 1) t + const
+  // with Q + 1 odd: the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups; phase 1 (lane = consecutive rows)
+  // is conflict free as well.  Plane 1 (8-byte units): row r at unit r + r/(2Q).  A 64-bit access is served per half
+  // warp, 16 lanes over 16 8-byte bank pairs: phase 1 writes 16 consecutive units (the pad only moves between half
+  // warps), phase 2 reads units Q t + i + (t + i/Q)/2 = 8 t + t/2 + const for Q = 8, distinct mod 16 for t = 0..15.
+  // (With the plane-0 padding r + r/Q in plane 1 every 64-bit store took 4 wavefronts instead of 2: ncu, run r4y.)
+  // All offsets are compile-time constants relative to two per-thread bases (i/Q even / odd).  Dynamic shared
+  // memory: Q = 16 needs 52 KB.
+  constexpr int UNITS = SynN3PSmem<K, Q>::UNITS;
+  constexpr int PADQ1 = SynN3PSmem<K, Q>::PADQ1;
+#if IAS_SYN3_STATIC
+  __shared__ __align__(16) float vs[SynN3PSmem<K, Q>::BYTES <= 48 * 1024 ? SynN3PSmem<K, Q>::BYTES / 4 : 4];
+#else
+  extern __shared__ __align__(16) float vs[];
+#endif
   float* const plane1 = vs + UNITS * 4;
 
   int b, tile;
@@ -959,30 +994,12 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
   const float* zb = z + (size_t)b * N * L;
 
   // ---- phase 1: modulate rows n_tile + DMIN + [0, ROWS) ----
-  float zk[PASSES][N];
-  if (n_tile + DMIN >= 0 && n_tile + DMIN + ROWS <= L) {
+  {
+    const bool interior = n_tile + DMIN >= 0 && n_tile + DMIN + ROWS <= L;
     // interior tile (all but the first and last of a sound): one pointer per band, constant offsets, no bounds logic
     const float* p0 = zb + (n_tile + DMIN + (int)threadIdx.x);
     const float* p1 = p0 + L;
     const float* p2_ = p1 + L;
-#pragma unroll
-    for (int i = 0; i < PASSES; ++i)
-      if ((i + 1) * PQ_THREADS <= ROWS || (int)threadIdx.x + i * PQ_THREADS < ROWS) {
-        zk[i][0] = __ldg(p0 + i * PQ_THREADS);
-        zk[i][1] = __ldg(p1 + i * PQ_THREADS);
-        zk[i][2] = __ldg(p2_ + i * PQ_THREADS);
-      }
-  } else {
-#pragma unroll
-    for (int i = 0; i < PASSES; ++i) {
-      const int row = (int)threadIdx.x + i * PQ_THREADS;
-      const int m = n_tile + DMIN + row;
-      const bool in = row < ROWS && m >= 0 && m < L;
-#pragma unroll
-      for (int k = 0; k < N; ++k) zk[i][k] = in ? __ldg(zb + (size_t)k * L + m) : 0.0f;
-    }
-  }
-  {
     // this thread's rows all have the parity of threadIdx.x (PQ_THREADS is even): order of the (a2, b2) pair
     const bool odd = (threadIdx.x & 1) != 0;
     P2 cx[N];
@@ -992,23 +1009,48 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
       cx[k] = odd ? p2(o.x, o.y) : p2(e.x, e.y);
     }
     const int unit0 = (int)threadIdx.x + (int)threadIdx.x / Q;
+    const int unit1 = (int)threadIdx.x + (int)threadIdx.x / PADQ1;
 #pragma unroll
-    for (int i = 0; i < PASSES; ++i) {
-      if ((i + 1) * PQ_THREADS <= ROWS || (int)threadIdx.x + i * PQ_THREADS < ROWS) {
-        // the stored pairs straight from packed multiply-adds (same k order per value as the scalar kernel)
-        P2 va = p2(0.0f, 0.0f), vb = va, vx = va;
+    for (int c0 = 0; c0 < PASSES; c0 += CH) {
+      float zk[CH][N];
+      if (interior) {
 #pragma unroll
-        for (int k = 0; k < N; ++k) {
-          const P2 zz = p2(zk[i][k], zk[i][k]);
-          const float2 ca = taps.cp[k * 4 + 0], cb = taps.cp[k * 4 + 1];
-          va = p2_fma(p2(ca.x, ca.y), zz, va);
-          vb = p2_fma(p2(cb.x, cb.y), zz, vb);
-          vx = p2_fma(cx[k], zz, vx);
+        for (int c = 0; c < CH; ++c) {
+          const int i = c0 + c;
+          if (i < PASSES && ((i + 1) * PQ_THREADS <= ROWS || (int)threadIdx.x + i * PQ_THREADS < ROWS)) {
+            zk[c][0] = __ldg(p0 + i * PQ_THREADS);
+            zk[c][1] = __ldg(p1 + i * PQ_THREADS);
+            zk[c][2] = __ldg(p2_ + i * PQ_THREADS);
+          }
         }
-        // row / Q = threadIdx.x / Q + i * (PQ_THREADS / Q): the pass offset is a compile-time constant
-        const int unit = unit0 + i * (PQ_THREADS + PQ_THREADS / Q);
-        *reinterpret_cast<ulonglong2*>(vs + unit * 4) = make_ulonglong2(va.v, vb.v);
-        *reinterpret_cast<unsigned long long*>(plane1 + unit * 2) = vx.v;
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int row = (int)threadIdx.x + (c0 + c) * PQ_THREADS;
+          const int m = n_tile + DMIN + row;
+          const bool in = row < ROWS && m >= 0 && m < L;
+#pragma unroll
+          for (int k = 0; k < N; ++k) zk[c][k] = in ? __ldg(zb + (size_t)k * L + m) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int i = c0 + c;
+        if (i < PASSES && ((i + 1) * PQ_THREADS <= ROWS || (int)threadIdx.x + i * PQ_THREADS < ROWS)) {
+          // the stored pairs straight from packed multiply-adds (same k order per value as the scalar kernel)
+          P2 va = p2(0.0f, 0.0f), vb = va, vx = va;
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            const P2 zz = p2(zk[c][k], zk[c][k]);
+            const float2 ca = taps.cp[k * 4 + 0], cb = taps.cp[k * 4 + 1];
+            va = p2_fma(p2(ca.x, ca.y), zz, va);
+            vb = p2_fma(p2(cb.x, cb.y), zz, vb);
+            vx = p2_fma(cx[k], zz, vx);
+          }
+          // row / Q = threadIdx.x / Q + i * (PQ_THREADS / Q): the pass offsets are compile-time constants
+          *reinterpret_cast<ulonglong2*>(vs + (unit0 + i * (PQ_THREADS + PQ_THREADS / Q)) * 4) = make_ulonglong2(va.v, vb.v);
+          *reinterpret_cast<unsigned long long*>(plane1 + (unit1 + i * (PQ_THREADS + PQ_THREADS / PADQ1)) * 2) = vx.v;
+        }
       }
     }
   }
@@ -1023,10 +1065,14 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
   for (int q = 0; q < Q; ++q) acc21[q] = p2(0.0f, 0.0f);
 #pragma unroll
   for (int q = 0; q < Q / 2; ++q) acc00[q] = p2(0.0f, 0.0f);
-  const int ubase = (int)threadIdx.x * (Q + 1);  // unit of row threadIdx.x * Q
+  const int ubase = (int)threadIdx.x * (Q + 1);  // plane-0 unit of row threadIdx.x * Q
+  // plane-1 unit of row Q t + i: Q t + i + (t + i/Q) / 2 = (i/Q even ? ubase1e : ubase1o) + i + (i/Q) / 2
+  const int ubase1e = (int)threadIdx.x * Q + ((int)threadIdx.x >> 1);
+  const int ubase1o = (int)threadIdx.x * Q + (((int)threadIdx.x + 1) >> 1);
 #pragma unroll
   for (int i = 0; i < Q + HALO; ++i) {
     const int unit = ubase + i + i / Q;
+    const int unit1 = PADQ1 == Q ? unit : (((i / Q) & 1) ? ubase1o : ubase1e) + i + (i / Q) / 2;
     const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(vs + unit * 4);
     P2 half[2];
     half[0].v = t.x;
@@ -1040,7 +1086,7 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
       }
     }
     P2 x;
-    x.v = *reinterpret_cast<const unsigned long long*>(plane1 + unit * 2);
+    x.v = *reinterpret_cast<const unsigned long long*>(plane1 + unit1 * 2);
 #pragma unroll
     for (int q2 = 0; q2 < Q / 2; ++q2) {
       const int d = i - 2 * q2;  // step 2 q2 meets this row at d, step 2 q2 + 1 at d - 1 (tap 0 in gc[0].y)
@@ -1214,7 +1260,7 @@ int launch_synthesis_small(const float* z, const float* proto_host, float* y, in
   return IAS_OK;
 }
 
-template <int K, int Q>
+template <int K, int Q, int MINB>
 int launch_synthesis_n3p(const float* z, const float* proto_host, float* y, int B, int L, cudaStream_t st) {
   constexpr int N = 3;
   TapsSynN3P<K> taps;
@@ -1237,9 +1283,15 @@ int launch_synthesis_n3p(const float* z, const float* proto_host, float* y, int 
   }
   constexpr int TILE_N = PQ_THREADS * Q;
   const int tiles = (L + TILE_N - 1) / TILE_N;
+  constexpr size_t smem = (IAS_SYN3_STATIC && SynN3PSmem<K, Q>::BYTES <= 48 * 1024) ? 0 : SynN3PSmem<K, Q>::BYTES;
+  if (smem > 48 * 1024) {
+    static unsigned long long seen = 0;
+    if (ias_first_use_on_device(seen))
+      IAS_CUDA(cudaFuncSetAttribute(k_pqmf_synthesis_n3p<K, Q, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   {
     ProfScope prof_(K_PQMF_SYNTHESIS, st);
-    k_pqmf_synthesis_n3p<K, Q><<<row_tile_grid(B, tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+    k_pqmf_synthesis_n3p<K, Q, MINB><<<row_tile_grid(B, tiles), PQ_THREADS, smem, st>>>(z, y, L, tiles, taps);
   }
   IAS_LAUNCH_CHECK("k_pqmf_synthesis_n3p");
   return IAS_OK;
@@ -1399,8 +1451,10 @@ extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const floa
       if (N == 3) {
         const char* pk = getenv("IAS_PQMF_SYNTH_PACKED");  // tuning switch: 0 = scalar FIR phase (bit-identical results)
         if (!pk || atoi(pk) != 0) {
-          if (q_env == 4) return launch_synthesis_n3p<63, 4>(z, proto_host, y, B, L, st);
-          return launch_synthesis_n3p<63, 8>(z, proto_host, y, B, L, st);
+          if (q_env == 4) return launch_synthesis_n3p<63, 4, 1>(z, proto_host, y, B, L, st);
+          if (q_env == 16) return launch_synthesis_n3p<63, 16, 1>(z, proto_host, y, B, L, st);  // capped at 94 registers: 0.373 ms
+          if (q_env == 88) return launch_synthesis_n3p<63, 8, 8>(z, proto_host, y, B, L, st);  // 63 registers, 8 CTAs per SM: 0.333 ms
+          return launch_synthesis_n3p<63, 8, IAS_SYN3_MINB>(z, proto_host, y, B, L, st);  // measured: 0.288 ms (scalar kernel 0.346)
         }
         if (q_env == 4) return launch_synthesis_small<3, 63, 4>(z, proto_host, y, B, L, st);
         return launch_synthesis_small<3, 63, 8>(z, proto_host, y, B, L, st);  // measured: Q=8 0.345 ms, Q=4 0.485, direct 0.494

@@ -287,6 +287,9 @@ def test_packed_n3_synthesis_is_bit_identical_to_the_scalar_kernel(cuda_device, 
                 outs[packed, q] = m.synthesis(zz)
         monkeypatch.delenv("IAS_PQMF_SYNTH_PACKED")
         monkeypatch.delenv("IAS_PQMF_SYNTH_Q")
+        monkeypatch.setenv("IAS_PQMF_SYNTH_Q", "16")
+        assert torch.equal(outs["1", "8"], m.synthesis(zz))
+        monkeypatch.delenv("IAS_PQMF_SYNTH_Q")
         assert torch.equal(outs["1", "8"], outs["0", "8"]) and torch.equal(outs["1", "4"], outs["0", "4"])
         assert torch.equal(outs["1", "8"], m.synthesis(zz))  # packed is what runs by default
         if L <= 4099:

@@ -25,8 +25,11 @@ def timed(fn, iters=20):
 m = ias_b200.PQMF(N=3).to(dev)
 z = m.analysis(x)
 ref = None
+CASES = (("1", "8"), ("1", "88"), ("1", "16"), ("1", "4"), ("0", "8"))
+if os.environ.get("IAS_SWEEP_ONLY"):  # A/B of variant libraries: the default shape and the scalar kernel only
+    CASES = (("1", os.environ["IAS_SWEEP_ONLY"]), ("0", "8"))
 for rep in range(2):
-    for packed, q in (("1", "8"), ("1", "4"), ("0", "8"), ("0", "4")):
+    for packed, q in CASES:
         os.environ["IAS_PQMF_SYNTH_PACKED"] = packed
         os.environ["IAS_PQMF_SYNTH_Q"] = q
         ms, y = timed(lambda: m.synthesis(z))
