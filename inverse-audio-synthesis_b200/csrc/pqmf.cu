@@ -942,9 +942,12 @@ template <int K, int Q>
 struct SynN3PSmem {
   static constexpr int ROWS = PQ_THREADS * Q + SynRows<3, K>::HALO;
   static constexpr int UNITS = ROWS + ROWS / Q + 1;         // plane 0: 16-byte units, row r at unit r + r/Q
-  static constexpr int PADQ1 = IAS_SYN3_PAD1 ? 2 * Q : Q;
-  static constexpr int UNITS1 = ROWS + ROWS / PADQ1 + 1;  // plane 1: 8-byte units, row r at unit r + r/(2Q)
-  static constexpr size_t BYTES = (size_t)UNITS * 16 + (size_t)UNITS1 * 8;
+  // plane 1: 8-byte units, row r at unit u1(r) = r + m + 8 (m / 8), m = r / (2Q)  (PAD1 = 0: r + r/Q as in plane 0)
+  __host__ __device__ static constexpr int u1(int r) {
+    return IAS_SYN3_PAD1 ? r + r / (2 * Q) + 8 * (r / (16 * Q)) : r + r / Q;
+  }
+  static constexpr int UNITS1 = u1(ROWS - 1) + 1;
+  static constexpr size_t BYTES = (size_t)UNITS * 16 + (size_t)((UNITS1 + 1) / 2 * 2) * 8;
 };
 
 template <int K>
@@ -973,14 +976,15 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
   constexpr int CH = Q <= 8 ? PASSES : 4;
   // Plane 0 (16-byte units): row r at unit r + r/Q.  Lane t of phase 2 reads rows Q t + i, i.e. units (Q + 1) t + const
   // with Q + 1 odd: the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups; phase 1 (lane = consecutive rows)
-  // is conflict free as well.  Plane 1 (8-byte units): row r at unit r + r/(2Q).  A 64-bit access is served per half
-  // warp, 16 lanes over 16 8-byte bank pairs: phase 1 writes 16 consecutive units (the pad only moves between half
-  // warps), phase 2 reads units Q t + i + (t + i/Q)/2 = 8 t + t/2 + const for Q = 8, distinct mod 16 for t = 0..15.
-  // (With the plane-0 padding r + r/Q in plane 1 every 64-bit store took 4 wavefronts instead of 2: ncu, run r4y.)
-  // All offsets are compile-time constants relative to two per-thread bases (i/Q even / odd).  Dynamic shared
-  // memory: Q = 16 needs 52 KB.
+  // is conflict free as well.  Plane 1 (8-byte units) is served per half warp, 16 lanes over 16 8-byte bank pairs.  Its
+  // pad may only change between the 16-row groups a half warp of phase 1 writes (m = r/16 for Q = 8), and phase 2 reads
+  // rows 8 (t + a) + i' (a = i/8): sixteen lanes cover eight or nine consecutive m, both rows of an m land 8 units
+  // apart, so the pads must differ mod 8 over eight consecutive m and by a multiple of 16 between m and m + 8:
+  // u1(r) = r + m + 8 (m/8).  (ncu source pages: with the plane-0 padding r + r/8 every 64-bit store took 4 wavefronts
+  // instead of 2, run r4y; with r + m alone the loads of every other row group did, run r4z.)  Phase-2 offsets are
+  // compile-time constants relative to one base per row group a = i/Q.  Dynamic shared memory: Q = 16 needs 52 KB.
   constexpr int UNITS = SynN3PSmem<K, Q>::UNITS;
-  constexpr int PADQ1 = SynN3PSmem<K, Q>::PADQ1;
+  using SM = SynN3PSmem<K, Q>;
 #if IAS_SYN3_STATIC
   __shared__ __align__(16) float vs[SynN3PSmem<K, Q>::BYTES <= 48 * 1024 ? SynN3PSmem<K, Q>::BYTES / 4 : 4];
 #else
@@ -1009,7 +1013,6 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
       cx[k] = odd ? p2(o.x, o.y) : p2(e.x, e.y);
     }
     const int unit0 = (int)threadIdx.x + (int)threadIdx.x / Q;
-    const int unit1 = (int)threadIdx.x + (int)threadIdx.x / PADQ1;
 #pragma unroll
     for (int c0 = 0; c0 < PASSES; c0 += CH) {
       float zk[CH][N];
@@ -1049,7 +1052,7 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
           }
           // row / Q = threadIdx.x / Q + i * (PQ_THREADS / Q): the pass offsets are compile-time constants
           *reinterpret_cast<ulonglong2*>(vs + (unit0 + i * (PQ_THREADS + PQ_THREADS / Q)) * 4) = make_ulonglong2(va.v, vb.v);
-          *reinterpret_cast<unsigned long long*>(plane1 + (unit1 + i * (PQ_THREADS + PQ_THREADS / PADQ1)) * 2) = vx.v;
+          *reinterpret_cast<unsigned long long*>(plane1 + SM::u1((int)threadIdx.x + i * PQ_THREADS) * 2) = vx.v;
         }
       }
     }
@@ -1066,13 +1069,15 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
 #pragma unroll
   for (int q = 0; q < Q / 2; ++q) acc00[q] = p2(0.0f, 0.0f);
   const int ubase = (int)threadIdx.x * (Q + 1);  // plane-0 unit of row threadIdx.x * Q
-  // plane-1 unit of row Q t + i: Q t + i + (t + i/Q) / 2 = (i/Q even ? ubase1e : ubase1o) + i + (i/Q) / 2
-  const int ubase1e = (int)threadIdx.x * Q + ((int)threadIdx.x >> 1);
-  const int ubase1o = (int)threadIdx.x * Q + (((int)threadIdx.x + 1) >> 1);
+  // plane-1 unit of row Q t + i = u1(Q (t + a)) + (i - Q a), a = i/Q: the pad is constant over the Q rows of a group
+  constexpr int GROUPS = (Q + HALO + Q - 1) / Q;
+  int ubase1[GROUPS];
+#pragma unroll
+  for (int a = 0; a < GROUPS; ++a) ubase1[a] = SM::u1(((int)threadIdx.x + a) * Q);
 #pragma unroll
   for (int i = 0; i < Q + HALO; ++i) {
     const int unit = ubase + i + i / Q;
-    const int unit1 = PADQ1 == Q ? unit : (((i / Q) & 1) ? ubase1o : ubase1e) + i + (i / Q) / 2;
+    const int unit1 = ubase1[i / Q] + (i % Q);
     const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(vs + unit * 4);
     P2 half[2];
     half[0].v = t.x;
