@@ -161,6 +161,11 @@ struct PoolArgs {
   // (Granlund-Montgomery: exact for 31-bit x); the divisors are launch constants, so the host prepares (m, sh)
   unsigned mS, shS, mP, shP;
 };
+// red.global.add.u64 on an address rebuilt from two 32-bit halves (the pooled epilogue keeps its accumulator addresses
+// in shared memory): through a C++ pointer nvcc no longer knows the address space and emits the generic-atomic dispatch
+__device__ __forceinline__ void red_global_add_u64(unsigned long long addr, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned magic_div(unsigned x, unsigned m, unsigned sh) { return __umulhi(x, m) >> sh; }
 inline void magic_for(unsigned d, unsigned& m, unsigned& sh) {  // d >= 2
   unsigned l = 1;
@@ -304,7 +309,9 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
   constexpr int SPAN = TILE_N * N + K - N + 4;
   constexpr int SPAN4 = (SPAN + 3) / 4;
   __shared__ __align__(16) float xs[Pad<S>::floats(SPAN4 * 4)];
-  __shared__ int s_bound[POOL ? N : 1][3];                        // per band: start of bin ilo+1, end of bin ilo, ilo
+  // per band: start of bin ilo+1, end of bin ilo, and the address of this sound's accumulator of bin ilo (8-byte
+  // aligned; bit 0 set when ilo is the last bin, i.e. there is no accumulator after it) -- one 128-bit load per band
+  __shared__ __align__(16) int4 s_bound[POOL ? N : 1];
 
   int b, tile;
   row_and_tile(tiles_per_row, b, tile);
@@ -333,9 +340,10 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
       const unsigned ilo = magic_div(first * (unsigned)pool.P, pool.mS, pool.shS);
       const unsigned num = (ilo + 1u) * (unsigned)pool.S;
       const unsigned q = magic_div(num, pool.mP, pool.shP);
-      s_bound[threadIdx.x][0] = (int)q;
-      s_bound[threadIdx.x][1] = (int)(q + (num - q * (unsigned)pool.P != 0u ? 1u : 0u));
-      s_bound[threadIdx.x][2] = (int)ilo;
+      const unsigned long long a =
+          (unsigned long long)__cvta_generic_to_global(pool.acc + (size_t)b * pool.P + ilo) | (ilo + 1u < (unsigned)pool.P ? 0ull : 1ull);
+      s_bound[threadIdx.x] = make_int4((int)q, (int)(q + (num - q * (unsigned)pool.P != 0u ? 1u : 0u)),
+                                       (int)(unsigned)a, (int)(unsigned)(a >> 32));
     }
   }
   __syncthreads();  // staged tile (register path), bin bounds and the mbarrier's initialisation are visible
@@ -497,20 +505,22 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
           for (int k = 0; k < N; ++k) acc[q][k] = 0.0f;
         }
     }
-    unsigned long long* bins = pool.acc + (size_t)b * pool.P;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       float a[Q];
 #pragma unroll
       for (int q = 0; q < Q; ++q) a[q] = fabsf(acc[q][k]);
-      const int s1 = s_bound[k][0], e0 = s_bound[k][1], ilo = s_bound[k][2];
+      const int4 bd = s_bound[k];
+      const int s1 = bd.x, e0 = bd.y;
+      const unsigned long long tagged = (unsigned long long)(unsigned)bd.z | ((unsigned long long)(unsigned)bd.w << 32);
+      const unsigned long long bin = tagged & ~7ull;  // global address of the accumulator of bin ilo
       const int wfirst = k * L + n_tile + warp * 32 * Q, wlast = wfirst + 32 * Q - 1;
       if (wlast < s1 || wfirst >= e0) {  // warp-uniform: the whole warp lies in one bin
         float t = a[0];
 #pragma unroll
         for (int q = 1; q < Q; ++q) t += a[q];
         const unsigned tot = __reduce_add_sync(0xffffffffu, pool_fixed(t));
-        if (lane == 0) atomicAdd(bins + ilo + (wfirst >= e0 ? 1 : 0), (unsigned long long)tot);
+        if (lane == 0) red_global_add_u64(bin + (wfirst >= e0 ? 8ull : 0ull), (unsigned long long)tot);
       } else {
         const int f0 = k * L + n0;
         float sum0 = 0.0f, sum1 = 0.0f;
@@ -522,8 +532,8 @@ k_pqmf_analysis(const float* __restrict__ x, const float* __restrict__ row_scale
         const unsigned t0s = __reduce_add_sync(0xffffffffu, pool_fixed(sum0));
         const unsigned t1s = __reduce_add_sync(0xffffffffu, pool_fixed(sum1));
         if (lane == 0) {
-          atomicAdd(bins + ilo, (unsigned long long)t0s);
-          if (ilo + 1 < pool.P) atomicAdd(bins + ilo + 1, (unsigned long long)t1s);
+          red_global_add_u64(bin, (unsigned long long)t0s);
+          if ((tagged & 1ull) == 0) red_global_add_u64(bin + 8ull, (unsigned long long)t1s);
         }
       }
     }
