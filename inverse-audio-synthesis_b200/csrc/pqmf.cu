@@ -709,9 +709,15 @@ k_pqmf_synthesis_cm(const float* __restrict__ z, float* __restrict__ y, int L, i
     const int m = n_tile + DMIN + (int)threadIdx.x;
     float zk[N];
     const bool in = (m >= 0 && m < L);
+    // one pointer walked from band to band: `zp + (size_t)k * L` costs a 64-bit multiply-add chain per load (ten
+    // integer instructions each, a quarter of the kernel's instructions at N = 16: ncu, run r4x; N = 8 0.338 -> 0.328 ms,
+    // N = 16 0.278 -> 0.276 ms -- that kernel waits on its stores, not on issue slots)
     const float* zp = z + (size_t)b * N * L + (in ? m : 0);
 #pragma unroll
-    for (int k = 0; k < N; ++k) zk[k] = in ? __ldg(zp + (size_t)k * L) : 0.0f;
+    for (int k = 0; k < N; ++k) {
+      zk[k] = in ? __ldg(zp) : 0.0f;
+      zp += L;
+    }
     float u[N];
     {
       P2 up[N / 2];  // two DCT outputs per FFMA2
@@ -837,7 +843,7 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
     const int m = n_tile + DMIN + row;
     const bool in = row < ROWS && m >= 0 && m < L;
 #pragma unroll
-    for (int k = 0; k < N; ++k) zk[i][k] = in ? __ldg(zb + (size_t)k * L + m) : 0.0f;
+    for (int k = 0; k < N; ++k) zk[i][k] = in ? __ldg(zb + (size_t)k * L + m) : 0.0f;  // (a walked pointer: N=4 0.389 vs 0.372 ms)
   }
 #pragma unroll
   for (int i = 0; i < PASSES; ++i) {

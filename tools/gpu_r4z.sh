@@ -29,5 +29,6 @@ NCU="ncu --set full --clock-control none --import-source on"
 timeout 600 $NCU -k regex:k_voice_audio -s 4 -c 1 -o gpurun_out/prof_voice_audio_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu audio exit $?"
 timeout 600 $NCU -k regex:k_pqmf_analysis -s 4 -c 1 -o gpurun_out/prof_k_pqmf_analysis_$TAG $CMD > gpurun_out/ncu_full_k_pqmf_analysis_$TAG.log 2>&1; echo "ncu analysis exit $?"
 timeout 300 $NCU -k regex:k_pqmf_synthesis -s 2 -c 1 -o gpurun_out/prof_k_pqmf_synthesis_n3_$TAG python tools/prof_pqmf.py > gpurun_out/ncu_syn3_$TAG.log 2>&1; echo "ncu synthesis N=3 exit $?"
+timeout 300 $NCU -k regex:k_pqmf_synthesis -s 5 -c 1 -o gpurun_out/prof_k_pqmf_synthesis_n16_$TAG python tools/prof_pqmf.py > gpurun_out/ncu_syn16_$TAG.log 2>&1; echo "ncu synthesis N=16 exit $?"
 timeout 600 python tools/bench_configs.py --skip-long > gpurun_out/configs_$TAG.jsonl 2> gpurun_out/configs_$TAG.err; echo "configs exit $?"
 cut -c1-260 gpurun_out/configs_$TAG.jsonl | head -12
