@@ -1139,6 +1139,149 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// synthesis, N = 4 (the default of pqmf.PQMF, pqmf.py:10), cosine-modulated form in packed fp32: the four taps that meet
+// (time step s, row s + d) are j = 4d .. 4d+3 on output phases 3, 2, 1, 0 and read elements 0 .. 3 of row half d & 1.
+// A row half is stored REVERSED (v3 v2 v1 v0), so that both operand pairs of a 128-bit shared load line up with
+// accumulator pairs in output order: (y[s][0], y[s][1]) += (g[4d+3], g[4d+2]) * (v3, v2) and
+// (y[s][2], y[s][3]) += (g[4d+1], g[4d]) * (v1, v0).  The kernel is bound by the L1 / shared-memory data pipe (ncu:
+// 90 % of its wavefront peak with Q consecutive steps per thread, which read BOTH halves of every row: 46 128-bit
+// loads per 32 outputs).  A step only ever reads the half whose parity is that of d, so a thread that owns Q steps of
+// ONE parity (s = s0 + par + 2q) reads one half per row: 30 loads per 32 outputs.  Lanes 2p / 2p+1 own the even / odd
+// steps of the same 2Q-step block and store 16-byte runs that interleave to contiguous memory.  Two 16-byte planes
+// (one per half), row r at unit r + 2 (r / 2Q): the eight lanes of a quarter warp (four pairs, 2Q rows apart, plus
+// the odd lanes' one-row shift) hit eight distinct bank groups, and so do the eight consecutive rows a quarter warp
+// stores in phase 1 (bank simulation: 0 conflicts).  Same rows, taps and accumulation order per output as
+// k_pqmf_synthesis_small<4>: bit-identical results.
+// ------------------------------------------------------------------------------------------------------------
+template <int K>
+struct TapsSynN4P {
+  static constexpr int ND = SynRows<4, K>::HALO + 1;
+  // modulation pairs per band k, c[k][r] as TapsSynSmall<4, K>::c: (c[res(0,3)], c[res(0,2)]), (c[res(0,1)], c[res(0,0)]),
+  // then the same for half 1
+  float2 cp[4 * 4];
+  float2 ga[ND];  // (g[4d+3], g[4d+2])
+  float2 gb[ND];  // (g[4d+1], g[4d])
+};
+
+template <int K, int Q>
+__global__ void __launch_bounds__(PQ_THREADS)
+k_pqmf_synthesis_n4p(const float* __restrict__ z, float* __restrict__ y, int L, int tiles_per_row, TapsSynN4P<K> taps) {
+  constexpr int N = 4;
+  using R = SynRows<N, K>;
+  constexpr int DMIN = R::DMIN, HALO = R::HALO;
+  constexpr int G = 2 * Q;  // steps (rows) per lane pair
+  static_assert(R::jb(DMIN) == 0, "pair tables assume taps 4d .. 4d+3");
+  static_assert(PQ_THREADS % G == 0 && G % 8 == 0, "phase-1 store offsets / bank layout");
+  constexpr int TILE_N = PQ_THREADS * Q;
+  constexpr int ROWS = TILE_N + HALO;
+  constexpr int PASSES = (ROWS + PQ_THREADS - 1) / PQ_THREADS;
+  constexpr int UNITS = ROWS + 2 * (ROWS / G) + 2;
+  __shared__ __align__(16) float vs[2 * UNITS * 4];
+
+  int b, tile;
+  row_and_tile(tiles_per_row, b, tile);
+  const int n_tile = tile * TILE_N;
+  const float* zb = z + (size_t)b * N * L;
+
+  // ---- phase 1: modulate rows n_tile + DMIN + [0, ROWS) ----
+  float zk[PASSES][N];
+  if (n_tile + DMIN >= 0 && n_tile + DMIN + ROWS <= L) {
+    // interior tile: one pointer per band, constant offsets, no bounds logic
+    const float* p0 = zb + (n_tile + DMIN + (int)threadIdx.x);
+    const float* p1 = p0 + L;
+    const float* p2_ = p1 + L;
+    const float* p3 = p2_ + L;
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i)
+      if ((i + 1) * PQ_THREADS <= ROWS || (int)threadIdx.x + i * PQ_THREADS < ROWS) {
+        zk[i][0] = __ldg(p0 + i * PQ_THREADS);
+        zk[i][1] = __ldg(p1 + i * PQ_THREADS);
+        zk[i][2] = __ldg(p2_ + i * PQ_THREADS);
+        zk[i][3] = __ldg(p3 + i * PQ_THREADS);
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      const int row = (int)threadIdx.x + i * PQ_THREADS;
+      const int m = n_tile + DMIN + row;
+      const bool in = row < ROWS && m >= 0 && m < L;
+#pragma unroll
+      for (int k = 0; k < N; ++k) zk[i][k] = in ? __ldg(zb + (size_t)k * L + m) : 0.0f;
+    }
+  }
+  {
+    const int unit0 = (int)threadIdx.x + 2 * ((int)threadIdx.x / G);
+#pragma unroll
+    for (int i = 0; i < PASSES; ++i) {
+      if ((i + 1) * PQ_THREADS <= ROWS || (int)threadIdx.x + i * PQ_THREADS < ROWS) {
+        P2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = p2(0.0f, 0.0f);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const P2 zz = p2(zk[i][k], zk[i][k]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 c = taps.cp[k * 4 + u];
+            v[u] = p2_fma(p2(c.x, c.y), zz, v[u]);
+          }
+        }
+        float* dst = vs + (unit0 + i * (PQ_THREADS + 2 * (PQ_THREADS / G))) * 4;
+        *reinterpret_cast<ulonglong2*>(dst) = make_ulonglong2(v[0].v, v[1].v);
+        *reinterpret_cast<ulonglong2*>(dst + UNITS * 4) = make_ulonglong2(v[2].v, v[3].v);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: Q time steps of one parity per thread (s = s0 + par + 2q), one row half streamed once ----
+  const int pr = (int)threadIdx.x >> 1, par = (int)threadIdx.x & 1;
+  const int s0 = n_tile + pr * G + par;  // this thread's first step; its row window starts at tile row pr * G + par
+  if (s0 >= L) return;
+  P2 acc01[Q], acc23[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc01[q] = acc23[q] = p2(0.0f, 0.0f);
+  // tile row pr*G + par + j lives at unit (G + 2) pr + par + j + 2 ((par + j) / G): constant offsets, except that the
+  // odd lane is one pad step ahead on the rows where par + j crosses a multiple of G
+  const float* base = vs + ((G + 2) * pr + par) * 4;
+  const int bump = par * 2 * 4;
+#pragma unroll
+  for (int j = 0; j < 2 * (Q - 1) + HALO + 1; ++j) {
+    // step q meets this row at d = j - 2q: the parity of d, i.e. the row half, is that of j for every q
+    const float* row = base + (j & 1) * UNITS * 4 + (j + 2 * (j / G)) * 4 + ((j % G == G - 1) ? bump : 0);
+    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(row);
+    P2 lo, hi;  // (v3, v2) and (v1, v0)
+    lo.v = t.x;
+    hi.v = t.y;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int d = j - 2 * q;
+      if (d >= 0 && d <= HALO) {
+        const float2 ga = taps.ga[d], gb = taps.gb[d];
+        acc01[q] = p2_fma(lo, p2(ga.x, ga.y), acc01[q]);
+        acc23[q] = p2_fma(hi, p2(gb.x, gb.y), acc23[q]);
+      }
+    }
+  }
+
+  float* yo = y + (size_t)b * L * N + (size_t)s0 * N;
+  const bool st_vec = (reinterpret_cast<uintptr_t>(y) & 15u) == 0;  // L * N and the run starts are multiples of 4 floats
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+    if (s0 + 2 * q < L) {
+      float f[4];
+      p2_unpack(acc01[q], f[0], f[1]);
+      p2_unpack(acc23[q], f[2], f[3]);
+      if (st_vec) {
+        *reinterpret_cast<float4*>(yo + 2 * q * N) = make_float4(f[0], f[1], f[2], f[3]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < N; ++p) yo[2 * q * N + p] = f[p];
+      }
+    }
+}
+
 __global__ void k_pqmf_synthesis_generic(const float* __restrict__ z, const float* __restrict__ G,
                                          float* __restrict__ y, int B, int L, int N, int K) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1318,6 +1461,37 @@ int launch_synthesis_n3p(const float* z, const float* proto_host, float* y, int 
   return IAS_OK;
 }
 
+template <int K, int Q>
+int launch_synthesis_n4p(const float* z, const float* proto_host, float* y, int B, int L, cudaStream_t st) {
+  constexpr int N = 4;
+  TapsSynN4P<K> taps;
+  using R = SynRows<N, K>;
+  for (int k = 0; k < N; ++k) {
+    auto c = [&](int h, int e) {
+      const int r = R::res(h, e);
+      return (float)(N * cos((2.0 * k + 1.0) * (3.14159265358979323846 / (2.0 * N)) * (r - (K - 2) / 2.0) -
+                             ((k & 1) ? -1.0 : 1.0) * 3.14159265358979323846 / 4.0));
+    };
+    for (int h = 0; h < 2; ++h) {
+      taps.cp[k * 4 + 2 * h + 0] = make_float2(c(h, 3), c(h, 2));
+      taps.cp[k * 4 + 2 * h + 1] = make_float2(c(h, 1), c(h, 0));
+    }
+  }
+  auto g = [&](int j) { return (j >= 0 && j < K) ? proto_host[j] : 0.0f; };
+  for (int d = 0; d < TapsSynN4P<K>::ND; ++d) {
+    taps.ga[d] = make_float2(g(4 * d + 3), g(4 * d + 2));
+    taps.gb[d] = make_float2(g(4 * d + 1), g(4 * d));
+  }
+  constexpr int TILE_N = PQ_THREADS * Q;
+  const int tiles = (L + TILE_N - 1) / TILE_N;
+  {
+    ProfScope prof_(K_PQMF_SYNTHESIS, st);
+    k_pqmf_synthesis_n4p<K, Q><<<row_tile_grid(B, tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_synthesis_n4p");
+  return IAS_OK;
+}
+
 }  // namespace
 }  // namespace ias
 
@@ -1466,6 +1640,11 @@ extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const floa
     if (N == 8) return launch_synthesis_cm<8, 63>(z, proto_host, y, B, L, st);
     if (!getenv("IAS_PQMF_SYNTH_DIRECT")) {  // tuning switch: direct form for N <= 4
       if (N == 4) {
+        const char* pk = getenv("IAS_PQMF_SYNTH_PACKED");  // tuning switch: 0 = scalar FIR phase (bit-identical results)
+        if (!pk || atoi(pk) != 0) {
+          if (q_env == 4) return launch_synthesis_n4p<63, 4>(z, proto_host, y, B, L, st);
+          return launch_synthesis_n4p<63, 8>(z, proto_host, y, B, L, st);
+        }
         if (q_env == 8) return launch_synthesis_small<4, 63, 8>(z, proto_host, y, B, L, st);
         return launch_synthesis_small<4, 63, 4>(z, proto_host, y, B, L, st);  // measured: Q=4 0.411 ms, Q=8 0.471, direct 0.643
       }

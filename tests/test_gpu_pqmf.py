@@ -271,14 +271,15 @@ def test_foreign_cosine_modulated_bank_with_stale_factors_takes_the_direct_form(
     assert OP.rel_err(y.cpu().numpy(), OP.synthesis(z.cpu().numpy(), G.astype(np.float64), N)) <= TOL
 
 
-def test_packed_n3_synthesis_is_bit_identical_to_the_scalar_kernel(cuda_device, monkeypatch):
-    """k_pqmf_synthesis_n3p (FFMA2 FIR phase, default for N = 3) runs the same multiply-add chains in the same order as
-    k_pqmf_synthesis_small<3>: equal bit for bit (torch.equal treats +-0 alike), interior and edge tiles, ragged lengths,
-    both Q."""
-    m = _mod(3, 0.15, cuda_device)
-    _, G = OP.design(3)
-    for B, L in ((2, 1), (2, 7), (3, 341), (2, 1024), (2, 1025), (2, 4099), (3, 58800), (1, 441000)):
-        zz = MG.pqmf_input(B, 3 * L, seed=300 + L % 97).reshape(B, 3, L).to(cuda_device)
+@pytest.mark.parametrize("N", [3, 4])
+def test_packed_small_n_synthesis_is_bit_identical_to_the_scalar_kernel(cuda_device, monkeypatch, N):
+    """k_pqmf_synthesis_n3p / _n4p (FFMA2 FIR phase, default for N = 3 and N = 4) run the same multiply-add chains in the
+    same order as k_pqmf_synthesis_small<N>: equal bit for bit (torch.equal treats +-0 alike), interior and edge tiles,
+    ragged lengths, every Q."""
+    m = _mod(N, 0.15, cuda_device)
+    _, G = OP.design(N)
+    for B, L in ((2, 1), (2, 7), (3, 341), (2, 1024), (2, 1025), (2, 4099), (3, 58800), (1, 330750)):
+        zz = MG.pqmf_input(B, N * L, seed=300 + L % 97).reshape(B, N, L).to(cuda_device)
         outs = {}
         for packed in ("1", "0"):
             for q in ("8", "4"):
@@ -286,12 +287,13 @@ def test_packed_n3_synthesis_is_bit_identical_to_the_scalar_kernel(cuda_device, 
                 monkeypatch.setenv("IAS_PQMF_SYNTH_Q", q)
                 outs[packed, q] = m.synthesis(zz)
         monkeypatch.delenv("IAS_PQMF_SYNTH_PACKED")
-        monkeypatch.delenv("IAS_PQMF_SYNTH_Q")
-        monkeypatch.setenv("IAS_PQMF_SYNTH_Q", "16")
-        assert torch.equal(outs["1", "8"], m.synthesis(zz))
+        if N == 3:
+            monkeypatch.setenv("IAS_PQMF_SYNTH_Q", "16")
+            assert torch.equal(outs["1", "8"], m.synthesis(zz))
         monkeypatch.delenv("IAS_PQMF_SYNTH_Q")
         assert torch.equal(outs["1", "8"], outs["0", "8"]) and torch.equal(outs["1", "4"], outs["0", "4"])
+        assert torch.equal(outs["1", "8"], outs["1", "4"])
         assert torch.equal(outs["1", "8"], m.synthesis(zz))  # packed is what runs by default
         if L <= 4099:
-            refy = OP.synthesis(zz.cpu().numpy(), G, 3)
+            refy = OP.synthesis(zz.cpu().numpy(), G, N)
             assert np.abs(outs["1", "8"][:, 0].cpu().numpy() - refy).max() <= TOL * max(np.abs(refy).max(), 1e-3)

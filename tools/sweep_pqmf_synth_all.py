@@ -21,6 +21,14 @@ def timed(fn, iters=20):
     return e0.elapsed_time(e1) / iters, out
 
 
+for packed, q in (("1", "8"), ("1", "4"), ("0", "4"), ("0", "8")):  # N = 4: packed kernel against the scalar one
+    os.environ["IAS_PQMF_SYNTH_PACKED"], os.environ["IAS_PQMF_SYNTH_Q"] = packed, q
+    m = ias_b200.PQMF(N=4).to(dev)
+    z = m.analysis(x)
+    mss, y = timed(lambda: m.synthesis(z))
+    print(f"N=4 packed={packed} Q={q}: synthesis {mss:.4f} ms ({8.0 * T * B / 1e6 / mss:.0f} GB/s)", flush=True)
+os.environ.pop("IAS_PQMF_SYNTH_PACKED")
+os.environ.pop("IAS_PQMF_SYNTH_Q")
 for rep in range(2):
     for N in (2, 3, 4, 8, 16):
         m = ias_b200.PQMF(N=N).to(dev)
