@@ -784,6 +784,144 @@ k_pqmf_synthesis_cm(const float* __restrict__ z, float* __restrict__ y, int L, i
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// synthesis, cosine-modulated form for N >= 8, second formulation of the FIR phase (round 2, session 3).
+// k_pqmf_synthesis_cm runs at 87 % of the L1 / shared-memory wavefront peak (ncu, run r4x), 52 % of those wavefronts
+// being the FIR phase's row loads: a time step reads HALO + 1 row halves (taps N rho .. N rho + N - 1 meet row
+// s + rho, half rho & 1), each of which a second step reads again.  Here a thread owns TWO steps of one parity,
+// s and s + 2, which share all but two of their row halves at the same tap alignment: HALO + 3 instead of
+// 2 (HALO + 1) half loads per two steps (N = 16: 6 instead of 8, N = 8: 10 instead of 16).  Lanes 2p / 2p+1 own the
+// even / odd steps of a four-step block; a CTA modulates 128 rows with all threads and runs the FIR phase on
+// (128 - HALO) / 4 * 4 steps with half of them.  Row halves are stored REVERSED, so that element pairs line up with
+// accumulator pairs in output order and the FIR phase is FFMA2s on (tap pair from a uniform register) x (pair of a
+// 128-bit shared load): acc[k], acc[k+1] += g[N rho + N-1-k], g[N rho + N-2-k] * half'[k], half'[k+1].
+// Row r starts at 16-byte unit (2N/4 + 1) r + 2 (r/8) + 4 (r/16): found by exhaustive search over small pads, free of
+// bank conflicts for the phase-1 stores (lanes = consecutive rows) and the phase-2 loads (lane pairs 4 rows apart).
+// Per output the taps are applied in ascending order as in the first formulation: bit-identical results.
+// ------------------------------------------------------------------------------------------------------------
+template <int N, int K>
+struct TapsSynCM2 {
+  static constexpr int NR = SynthGeom<N, K>::omax() - SynthGeom<N, K>::omin() + 1;
+  float c[N * N];            // (N / sqrt 2) cos((2k+1)(2m+1) pi / (4N)), [k][m]
+  float2 gp[NR * (N / 2)];   // [rho][k/2] = (g[N rho + N-1-k], g[N rho + N-2-k]), k even; 0 beyond tap K-1
+};
+
+template <int N>
+__host__ __device__ constexpr int cm2_row_unit(int r) { return (2 * N / 4 + 1) * r + 2 * (r / 8) + 4 * (r / 16); }
+
+template <int N, int K>
+__global__ void __launch_bounds__(PQ_THREADS)
+k_pqmf_synthesis_cm2(const float* __restrict__ z, float* __restrict__ y, int L, int tiles_per_row, TapsSynCM2<N, K> taps) {
+  using Geo = SynthGeom<N, K>;
+  using UF = UnfoldCM<N, K>;
+  constexpr int DMIN = Geo::omin();
+  constexpr int HALO = Geo::omax() - DMIN;
+  constexpr int TILE_N = (PQ_THREADS - HALO) / 4 * 4;  // time steps per CTA (whole four-step blocks)
+  constexpr int ACTIVE = TILE_N / 2;                   // FIR-phase threads
+  static_assert(N % 4 == 0 && Geo::phase(0) == N - 1 && Geo::offset(N) - Geo::offset(0) == 1, "tap blocks of N per row");
+  static_assert(TILE_N - 1 + HALO < PQ_THREADS, "every row is modulated by one thread");
+  __shared__ __align__(16) float vs[(cm2_row_unit<N>(PQ_THREADS - 1) + 2 * N / 4) * 4];
+
+  int b, tile;
+  row_and_tile(tiles_per_row, b, tile);
+  const int n_tile = tile * TILE_N;
+
+  {
+    const int m = n_tile + DMIN + (int)threadIdx.x;
+    float zk[N];
+    const bool in = (m >= 0 && m < L);
+    const float* zp = z + (size_t)b * N * L + (in ? m : 0);  // walked from band to band (no 64-bit multiply per load)
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      zk[k] = in ? __ldg(zp) : 0.0f;
+      zp += L;
+    }
+    float u[N];
+    {
+      P2 up[N / 2];  // two DCT outputs per FFMA2
+#pragma unroll
+      for (int m2 = 0; m2 < N / 2; ++m2) up[m2] = p2(0.0f, 0.0f);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const P2 zz = p2(zk[k], zk[k]);
+#pragma unroll
+        for (int m2 = 0; m2 < N / 2; ++m2) {
+          const float2 t = reinterpret_cast<const float2*>(taps.c)[(k * N) / 2 + m2];
+          up[m2] = p2_fma(p2(t.x, t.y), zz, up[m2]);
+        }
+      }
+#pragma unroll
+      for (int m2 = 0; m2 < N / 2; ++m2) p2_unpack(up[m2], u[2 * m2], u[2 * m2 + 1]);
+    }
+    float v[2 * N];
+#pragma unroll
+    for (int r = 0; r < 2 * N; ++r) {
+      const float a = u[UF::mp(r)], bb = u[N - 1 - UF::mp(r)];
+      const float sgn = UF::pos(r) ? a + bb : a - bb;
+      v[r] = UF::neg(r) ? -sgn : sgn;
+    }
+    // half h reversed: position k of the half holds v[N h + N-1-k]
+    float* row = vs + cm2_row_unit<N>((int)threadIdx.x) * 4;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int k = 0; k < N; k += 4)
+        *reinterpret_cast<float4*>(row + h * N + k) = make_float4(v[N * h + N - 1 - k], v[N * h + N - 2 - k],
+                                                                  v[N * h + N - 3 - k], v[N * h + N - 4 - k]);
+  }
+  __syncthreads();
+
+  if ((int)threadIdx.x >= ACTIVE) return;
+  const int pr = (int)threadIdx.x >> 1, par = (int)threadIdx.x & 1;
+  const int sA = 4 * pr + par;  // tile-relative first step; the second one is sA + 2
+  if (n_tile + sA >= L) return;
+  P2 acc[2][N / 2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int k2 = 0; k2 < N / 2; ++k2) acc[q][k2] = p2(0.0f, 0.0f);
+#pragma unroll
+  for (int j = 0; j < HALO + 3; ++j) {
+    // row sA + j is met by step sA at rho = j and by step sA + 2 at rho = j - 2: same parity, same half
+    const float* half = vs + cm2_row_unit<N>(sA + j) * 4 + (j & 1) * N;
+    P2 w[N / 2];
+#pragma unroll
+    for (int k = 0; k < N; k += 4) {
+      const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(half + k);
+      w[k / 2].v = t.x;
+      w[k / 2 + 1].v = t.y;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int rho = j - 2 * q;
+      if (rho >= 0 && rho <= HALO) {
+#pragma unroll
+        for (int k2 = 0; k2 < N / 2; ++k2) {
+          const float2 g = taps.gp[rho * (N / 2) + k2];
+          acc[q][k2] = p2_fma(w[k2], p2(g.x, g.y), acc[q][k2]);
+        }
+      }
+    }
+  }
+  const bool st_vec = (reinterpret_cast<uintptr_t>(y) & 15u) == 0;  // L * N and the run starts are multiples of 4 floats
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int n = n_tile + sA + 2 * q;
+    if (n < L) {
+      float f[N];
+#pragma unroll
+      for (int k2 = 0; k2 < N / 2; ++k2) p2_unpack(acc[q][k2], f[2 * k2], f[2 * k2 + 1]);
+      float* yo = y + (size_t)b * L * N + (size_t)n * N;
+      if (st_vec) {
+        store_run<N>(yo, f, (reinterpret_cast<uintptr_t>(yo) & 31u) == 0);
+      } else {
+#pragma unroll
+        for (int p = 0; p < N; ++p) yo[p] = f[p];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // synthesis, cosine-modulated form for small N (2, 3, 4): same factorisation as above with the N -> 2N modulation
 // done directly (2 N^2 multiply-adds per time step), and Q consecutive time steps per thread in the FIR phase so
 // that each modulated row read from shared memory serves Q time steps.  The N taps that meet one (time step, row)
@@ -1406,6 +1544,27 @@ int launch_synthesis_cm(const float* z, const float* proto_host, float* y, int B
   return IAS_OK;
 }
 
+template <int N, int K>
+int launch_synthesis_cm2(const float* z, const float* proto_host, float* y, int B, int L, cudaStream_t st) {
+  TapsSynCM2<N, K> taps;
+  for (int k = 0; k < N; ++k)
+    for (int m = 0; m < N; ++m)
+      taps.c[k * N + m] = (float)(cos((2.0 * k + 1.0) * (2.0 * m + 1.0) * 3.14159265358979323846 / (4.0 * N)) *
+                                  0.70710678118654752440 * N);
+  auto g = [&](int j) { return (j >= 0 && j < K) ? proto_host[j] : 0.0f; };
+  for (int rho = 0; rho < TapsSynCM2<N, K>::NR; ++rho)
+    for (int k = 0; k < N; k += 2)
+      taps.gp[rho * (N / 2) + k / 2] = make_float2(g(N * rho + N - 1 - k), g(N * rho + N - 2 - k));
+  constexpr int TILE_N = (PQ_THREADS - (SynthGeom<N, K>::omax() - SynthGeom<N, K>::omin())) / 4 * 4;
+  const int tiles = (L + TILE_N - 1) / TILE_N;
+  {
+    ProfScope prof_(K_PQMF_SYNTHESIS, st);
+    k_pqmf_synthesis_cm2<N, K><<<row_tile_grid(B, tiles), PQ_THREADS, 0, st>>>(z, y, L, tiles, taps);
+  }
+  IAS_LAUNCH_CHECK("k_pqmf_synthesis_cm2");
+  return IAS_OK;
+}
+
 template <int N, int K, int Q>
 int launch_synthesis_small(const float* z, const float* proto_host, float* y, int B, int L, cudaStream_t st) {
   TapsSynSmall<N, K> taps;
@@ -1636,6 +1795,11 @@ extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const floa
   if (const char* e = getenv("IAS_PQMF_SYNTH_Q")) q_env = atoi(e);
   if (proto_host && !cm_design_matches(G_host, proto_host, nullptr, N, K, true)) proto_host = nullptr;
   if (proto_host && K == 63) {  // G is the designed filter: cosine-modulated form
+    const char* cm2 = getenv("IAS_PQMF_SYNTH_CM2");  // tuning switch: 0 = one step per thread (bit-identical results)
+    if (!cm2 || atoi(cm2) != 0) {
+      if (N == 16) return launch_synthesis_cm2<16, 63>(z, proto_host, y, B, L, st);
+      if (N == 8) return launch_synthesis_cm2<8, 63>(z, proto_host, y, B, L, st);
+    }
     if (N == 16) return launch_synthesis_cm<16, 63>(z, proto_host, y, B, L, st);
     if (N == 8) return launch_synthesis_cm<8, 63>(z, proto_host, y, B, L, st);
     if (!getenv("IAS_PQMF_SYNTH_DIRECT")) {  // tuning switch: direct form for N <= 4

@@ -297,3 +297,22 @@ def test_packed_small_n_synthesis_is_bit_identical_to_the_scalar_kernel(cuda_dev
         if L <= 4099:
             refy = OP.synthesis(zz.cpu().numpy(), G, N)
             assert np.abs(outs["1", "8"][:, 0].cpu().numpy() - refy).max() <= TOL * max(np.abs(refy).max(), 1e-3)
+
+
+@pytest.mark.parametrize("N", [8, 16])
+def test_two_step_cosine_modulated_synthesis_is_bit_identical_to_the_one_step_kernel(cuda_device, monkeypatch, N):
+    """k_pqmf_synthesis_cm2 (two same-parity steps per thread, reversed row halves, FFMA2 FIR phase; default for
+    N = 8, 16) applies the same taps in the same order per output as k_pqmf_synthesis_cm."""
+    m = _mod(N, 0.15, cuda_device)
+    _, G = OP.design(N)
+    for B, L in ((2, 1), (2, 3), (3, 119), (2, 120), (2, 121), (3, 124), (2, 125), (2, 1251), (3, 11025), (1, 82688)):
+        zz = MG.pqmf_input(B, N * L, seed=500 + L % 89).reshape(B, N, L).to(cuda_device)
+        monkeypatch.setenv("IAS_PQMF_SYNTH_CM2", "0")
+        y1 = m.synthesis(zz)
+        monkeypatch.setenv("IAS_PQMF_SYNTH_CM2", "1")
+        y2 = m.synthesis(zz)
+        monkeypatch.delenv("IAS_PQMF_SYNTH_CM2")
+        assert torch.equal(y1, y2) and torch.equal(y2, m.synthesis(zz))
+        if L <= 1251:
+            refy = OP.synthesis(zz.cpu().numpy(), G, N)
+            assert np.abs(y2[:, 0].cpu().numpy() - refy).max() <= TOL * max(np.abs(refy).max(), 1e-3)

@@ -29,6 +29,15 @@ for packed, q in (("1", "8"), ("1", "4"), ("0", "4"), ("0", "8")):  # N = 4: pac
     print(f"N=4 packed={packed} Q={q}: synthesis {mss:.4f} ms ({8.0 * T * B / 1e6 / mss:.0f} GB/s)", flush=True)
 os.environ.pop("IAS_PQMF_SYNTH_PACKED")
 os.environ.pop("IAS_PQMF_SYNTH_Q")
+for rep in range(2):  # N = 8, 16: two steps per thread (cm2) against one (cm)
+    for N in (8, 16):
+        for cm2 in ("1", "0"):
+            os.environ["IAS_PQMF_SYNTH_CM2"] = cm2
+            m = ias_b200.PQMF(N=N).to(dev)
+            z = m.analysis(x)
+            mss, y = timed(lambda: m.synthesis(z))
+            print(f"N={N} cm2={cm2}: synthesis {mss:.4f} ms ({8.0 * T * B / 1e6 / mss:.0f} GB/s)", flush=True)
+os.environ.pop("IAS_PQMF_SYNTH_CM2")
 for rep in range(2):
     for N in (2, 3, 4, 8, 16):
         m = ias_b200.PQMF(N=N).to(dev)
