@@ -165,9 +165,13 @@ IAS_API int ias_pqmf_analysis_pooled(const float* x, const float* H_dev, const f
 
 /* PQMF.synthesis (pqmf.py:52-55): zero-stuff by N with gain N, then the N->1 FIR G = [N][K] (buffer G[0]).
  * y[b][t], t < L*N.  proto_host[K] (host, optional) is the same signed prototype as in ias_pqmf_analysis: the caller
- * passes it when G is the filter PQMF.__init__ designs (pqmf.py:18-30), and N = 8 / 16 then run the cosine-modulated
- * form (size-N DCT-IV per time step + 63 multiply-adds, instead of 63 N); NULL = direct form, valid for any G.
- * As for the analysis, proto_host is honoured only when G_host is the PQMF.__init__ design it factorises. */
+ * passes it when G is the filter PQMF.__init__ designs (pqmf.py:18-30), and N = 2, 3, 4, 8, 16 then run the
+ * cosine-modulated form (N -> 2N modulation per time step + 63 multiply-adds, instead of 63 N; packed fp32 for
+ * N = 3, 4, 8, 16); NULL = direct form, valid for any G.
+ * As for the analysis, proto_host is honoured only when G_host is the PQMF.__init__ design it factorises.
+ * Tuning / reference switches read from the environment at call time (results are bit-identical either way):
+ * IAS_PQMF_SYNTH_PACKED=0 (N = 3, 4: scalar FIR phase), IAS_PQMF_SYNTH_CM2=0 (N = 8, 16: one time step per thread),
+ * IAS_PQMF_SYNTH_Q=<steps per thread>, IAS_PQMF_SYNTH_DIRECT=1 (N <= 4: direct form). */
 IAS_API int ias_pqmf_synthesis(const float* z, const float* G_dev, const float* G_host, const float* proto_host, float* y,
                        int B, int L, int N, int K, ias_stream_t stream);
 
