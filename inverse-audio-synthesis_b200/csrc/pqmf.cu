@@ -1079,18 +1079,15 @@ k_pqmf_synthesis_small(const float* __restrict__ z, float* __restrict__ y, int L
 // Taps outside [0, K) are zeros of the pair tables (their products add +0 to a finite accumulator).
 // ------------------------------------------------------------------------------------------------------------
 // tuning builds (tools/gpu_r4e.sh, one box, 1024 x 4 s): plane-1 padding every Q rows as in plane 0 (PAD1=0) / register
-// cap through __launch_bounds__(128, MINB) / static shared memory.  Measured: uncapped (75 registers, 6 CTAs per SM)
-// 0.288 ms; MINB=7 (70 registers, 7 CTAs per SM) 0.324 ms -- ptxas pays for the five registers with a serialised load
-// schedule that costs far more than the seventh CTA brings; MINB=7 with PAD1=0 0.318; static instead of dynamic shared
-// memory: no difference.
+// cap through __launch_bounds__(128, MINB).  Measured: uncapped (75 registers, 6 CTAs per SM) 0.288 ms; MINB=7
+// (70 registers, 7 CTAs per SM) 0.324 ms -- ptxas pays for the five registers with a serialised load schedule that
+// costs far more than the seventh CTA brings; MINB=7 with PAD1=0 0.318; static instead of dynamic shared memory: no
+// difference (not kept).
 #ifndef IAS_SYN3_PAD1
 #define IAS_SYN3_PAD1 1
 #endif
 #ifndef IAS_SYN3_MINB
 #define IAS_SYN3_MINB 1
-#endif
-#ifndef IAS_SYN3_STATIC
-#define IAS_SYN3_STATIC 0
 #endif
 template <int K, int Q>
 struct SynN3PSmem {
@@ -1139,11 +1136,7 @@ k_pqmf_synthesis_n3p(const float* __restrict__ z, float* __restrict__ y, int L, 
   // compile-time constants relative to one base per row group a = i/Q.  Dynamic shared memory: Q = 16 needs 52 KB.
   constexpr int UNITS = SynN3PSmem<K, Q>::UNITS;
   using SM = SynN3PSmem<K, Q>;
-#if IAS_SYN3_STATIC
-  __shared__ __align__(16) float vs[SynN3PSmem<K, Q>::BYTES <= 48 * 1024 ? SynN3PSmem<K, Q>::BYTES / 4 : 4];
-#else
   extern __shared__ __align__(16) float vs[];
-#endif
   float* const plane1 = vs + UNITS * 4;
 
   int b, tile;
@@ -1606,7 +1599,7 @@ int launch_synthesis_n3p(const float* z, const float* proto_host, float* y, int 
   }
   constexpr int TILE_N = PQ_THREADS * Q;
   const int tiles = (L + TILE_N - 1) / TILE_N;
-  constexpr size_t smem = (IAS_SYN3_STATIC && SynN3PSmem<K, Q>::BYTES <= 48 * 1024) ? 0 : SynN3PSmem<K, Q>::BYTES;
+  constexpr size_t smem = SynN3PSmem<K, Q>::BYTES;
   if (smem > 48 * 1024) {
     static unsigned long long seen = 0;
     if (ias_first_use_on_device(seen))
@@ -1816,9 +1809,9 @@ extern "C" int ias_pqmf_synthesis(const float* z, const float* G_dev, const floa
         const char* pk = getenv("IAS_PQMF_SYNTH_PACKED");  // tuning switch: 0 = scalar FIR phase (bit-identical results)
         if (!pk || atoi(pk) != 0) {
           if (q_env == 4) return launch_synthesis_n3p<63, 4, 1>(z, proto_host, y, B, L, st);
-          if (q_env == 16) return launch_synthesis_n3p<63, 16, 1>(z, proto_host, y, B, L, st);  // capped at 94 registers: 0.373 ms
+          if (q_env == 16) return launch_synthesis_n3p<63, 16, 1>(z, proto_host, y, B, L, st);  // 94 registers, 52 KB: 0.373 ms
           if (q_env == 88) return launch_synthesis_n3p<63, 8, 8>(z, proto_host, y, B, L, st);  // 63 registers, 8 CTAs per SM: 0.333 ms
-          return launch_synthesis_n3p<63, 8, IAS_SYN3_MINB>(z, proto_host, y, B, L, st);  // measured: 0.288 ms (scalar kernel 0.346)
+          return launch_synthesis_n3p<63, 8, IAS_SYN3_MINB>(z, proto_host, y, B, L, st);  // measured: 0.272 ms (scalar kernel 0.345)
         }
         if (q_env == 4) return launch_synthesis_small<3, 63, 4>(z, proto_host, y, B, L, st);
         return launch_synthesis_small<3, 63, 8>(z, proto_host, y, B, L, st);  // measured: Q=8 0.345 ms, Q=4 0.485, direct 0.494
